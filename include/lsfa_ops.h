@@ -1,0 +1,206 @@
+/*
+ * lsfa_ops.h - C ABI of the B200-native LSFA non-key-frame propagation path.
+ *
+ * Drop-in boundary for ONE path of hustvl/LSFA (dff_rfcn): compressed-stream motion
+ * vectors -> stride-16 flow -> warp grid -> bilinear sample of the key-frame feature
+ * -> x scale map -> (+ residual 1x1 conv) -> aggregation with the current-frame feature.
+ * File:line citations are relative to the reference tree; SYM =
+ * dff_rfcn/symbols/resnet_v1_101_flownet_rfcn.py.
+ *
+ * Conventions (mirroring how MXNet hands tensors to an operator):
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never
+ *     allocates, frees or synchronises; work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream) of the calling thread's current
+ *     device;
+ *   - return value 0 = LSFA_OK, negative = error; the message is available from the
+ *     thread-local lsfa_last_error() (same shape as MXGetLastError());
+ *   - `req` follows MXNet's OpReqType: 0 kNullOp (nothing is written), 1 kWriteTo,
+ *     2 kWriteInplace (treated as kWriteTo), 3 kAddTo (out += result);
+ *   - entry points are re-entrant: no global mutable state, safe from N host threads
+ *     driving N devices (tester.py:301-309 runs one thread per GPU).
+ */
+#ifndef LSFA_OPS_H_
+#define LSFA_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSFA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LSFA_API __attribute__((visibility("default")))
+#else
+#define LSFA_API
+#endif
+
+/* error codes */
+#define LSFA_OK             0
+#define LSFA_E_BADARG     (-1)  /* NULL where a pointer is required, unknown enum value */
+#define LSFA_E_SHAPE      (-2)  /* non-positive / inconsistent dimensions */
+#define LSFA_E_ALIGN      (-3)  /* pointer or channel count violates a vector-width rule */
+#define LSFA_E_CUDA       (-4)  /* launch failed (cudaPeekAtLastError) */
+#define LSFA_E_UNSUPPORTED (-5) /* valid request this build cannot serve */
+
+/* MXNet OpReqType */
+#define LSFA_REQ_NULL    0
+#define LSFA_REQ_WRITE   1
+#define LSFA_REQ_INPLACE 2
+#define LSFA_REQ_ADD     3
+
+/* stride-16 reduction of the MV / residual image (lib/utils/image.py:220-222) */
+#define LSFA_POOL_CENTRE2X2 0   /* what cv2.resize(fx=1/16, INTER_LINEAR) computes: parity mode */
+#define LSFA_POOL_AVG16     1   /* literal 16x16 block mean */
+
+/* where the sampling positions of the fused op come from */
+#define LSFA_FLOW_PREPOOLED 0   /* flow (N,2,H,W) f32 in feature cells = `motion_vector` of SYM:571 */
+#define LSFA_FLOW_RAW_I32   1   /* raw MV (N,h,w,2) int32 pixels, pooled in-kernel */
+#define LSFA_FLOW_RAW_F32   2   /* raw MV (N,h,w,2) float32 pixels, pooled in-kernel */
+#define LSFA_FLOW_GRID      3   /* normalised grid (N,2,H,W) f32 = output of GridGenerator */
+
+/* aggregation of src0 = warp(key)[*scale][+rnet(res)] with src1 = cur */
+#define LSFA_W_NONE   0   /* out = src0                         (SYM:571-576, 678-680) */
+#define LSFA_W_ADD    1   /* out = cur + src0                   (fuse_small_net 'add', SYM:236) */
+#define LSFA_W_MEAN   2   /* out = 0.5*(src0 + cur)             (SYM:315,476) */
+#define LSFA_W_LOGITS 3   /* softmax over {logit_warp, logit_cur} (Nq_net tail, SYM:104-108) */
+#define LSFA_W_COSINE 4   /* logits from cosine of embeddings   (Fgfa_net, SYM:111-116,132-148) */
+
+/* memory layout / element type of the feature tensors (key, scale_map, cur, out, emb_*) */
+#define LSFA_LAYOUT_NCHW_F32  0   /* MXNet's layout: the drop-in variant */
+#define LSFA_LAYOUT_NHWC_F32  1
+#define LSFA_LAYOUT_NHWC_BF16 2   /* channel-vectorised fast path; fp32 accumulate */
+
+/*
+ * Argument block of the fused operator.  Zero-initialise, set struct_bytes =
+ * sizeof(LsfaAggArgs), fill what the chosen modes need, leave the rest NULL/0.
+ *
+ *   src0[n] = BilinearSampler(key[key_index ? key_index[n] : n],
+ *                             GridGenerator_warp(flow[n]))          SYM:571-572
+ *             [* scale_map[n]]                                      SYM:308,470,680
+ *             [+ rnet_w . res[n] + rnet_b]                          SYM:66,576
+ *   out[n]  = blend(src0[n], cur[n]) by weight_mode; bypass[n] != 0 -> out[n] = cur[n]
+ *             (ChooseFeat, operator_py/choose_feat.py:23-31)
+ */
+typedef struct LsfaAggArgs {
+  int32_t struct_bytes;      /* = sizeof(LsfaAggArgs): ABI guard */
+  int32_t layout;            /* LSFA_LAYOUT_* */
+  int32_t N, C, H, W;        /* output frames, channels, output (= flow/grid) height, width */
+  int32_t key_h, key_w;      /* spatial size of key planes; 0,0 = same as H,W */
+  int32_t num_keys;          /* number of key features behind `key` (for index checking); 0 = N */
+
+  const void*    key;        /* (num_keys,C,key_h,key_w) | NHWC (num_keys,key_h,key_w,C) */
+  const int32_t* key_index;  /* (N,) optional: which key feature frame n samples (tile_as.py:16-19) */
+
+  int32_t flow_kind;         /* LSFA_FLOW_* */
+  const void* flow;          /* per flow_kind */
+  int32_t mv_h, mv_w;        /* raw MV image size (unpadded); H = ceil(mv_h/16), W = ceil(mv_w/16) */
+  double  im_scale;          /* image.py:224: flow = pooled * im_scale / 16 */
+  int32_t pool_mode;         /* LSFA_POOL_* */
+
+  const void*  scale_map;    /* optional, same shape/layout as out */
+  const float* res;          /* optional pooled residual (N,3,H,W) f32 (always NCHW) */
+  const float* rnet_w;       /* (C,3) f32 = rnet_conv0 weight (C,3,1,1) */
+  const float* rnet_b;       /* (C,)  f32 */
+
+  const void*  cur;          /* same shape/layout as out; required unless weight_mode == NONE */
+  int32_t weight_mode;       /* LSFA_W_* */
+  const float* logits;       /* (N,2,H,W) f32: [n,0] = warp logit, [n,1] = cur logit */
+  const void*  emb_warp;     /* (N,E,H,W) | NHWC (N,H,W,E): embedding of the warped feature */
+  const void*  emb_cur;      /* embedding of the current feature */
+  int32_t E;                 /* embedding channels (2048 in SYM:126) */
+  const uint8_t* bypass;     /* (N,) optional */
+
+  void*   out;               /* (N,C,H,W) | (N,H,W,C) */
+  int32_t req;               /* LSFA_REQ_* */
+
+  void*   workspace;         /* lsfa_warp_scale_aggregate_workspace_bytes() bytes, or NULL if 0 */
+  size_t  workspace_bytes;
+
+  int32_t force_generic;     /* debug/ablation: 1 = skip the plane-resident fast kernel */
+} LsfaAggArgs;
+
+LSFA_API int         lsfa_version(void);
+LSFA_API const char* lsfa_last_error(void);   /* thread-local, never NULL */
+
+/* a3+a5+a6 - replaces the CPU half of transform_mv_res for the MV
+ * (lib/utils/image.py:207-215,220-228): zero-pad to 16, stride-16 reduction in float64,
+ * times im_scale/16, HWC -> (N,2,H,W) float32 with ch0 = x, ch1 = y.
+ * mv: (N,h,w,2) int32 | float32, already resized by im_scale (stage 1).  H=ceil(h/16). */
+LSFA_API int lsfa_mv_pool_i32(const int32_t* mv, float* flow, int N, int h, int w,
+                     double im_scale, int mode, void* stream);
+LSFA_API int lsfa_mv_pool_f32(const float* mv, float* flow, int N, int h, int w,
+                     double im_scale, int mode, void* stream);
+
+/* a3+a4+a5 for the residual (image.py:207-222), including the in-place channel aliasing of
+ * image.py:217-218.  res: (N,h,w,3); means[3], pixel_scale as config.network.PIXEL_MEANS /
+ * PIXEL_SCALE; out (N,3,H,W) float32. */
+LSFA_API int lsfa_res_pool_i32(const int32_t* res, float* out, int N, int h, int w,
+                      const double* means, double pixel_scale, int mode, void* stream);
+LSFA_API int lsfa_res_pool_f32(const float* res, float* out, int N, int h, int w,
+                      const double* means, double pixel_scale, int mode, void* stream);
+
+/* a1+a2 - replaces lib/utils/image.py:52-60 (sign, optional h-flip) and :204 (cv2.resize
+ * by im_scale, INTER_LINEAR, float32) for the MV.  in (N,h,w,2) int32 as coviar returns it;
+ * out (N,oh,ow,2) float32 with oh = cvRound(h*im_scale).  negate=1 applies image.py:54. */
+LSFA_API int lsfa_mv_prepare_i32(const int32_t* mv_coviar, float* mv_out, int N, int h, int w,
+                        int oh, int ow, double im_scale, int negate, int hflip, void* stream);
+
+/* a7 - mx.sym.GridGenerator(data=flow, transform_type='warp') (SYM:306,320,468,571,678).
+ * flow, grid: (N,2,H,W) float32. */
+LSFA_API int lsfa_grid_generator_warp_f32(const float* flow, float* grid, int N, int H, int W,
+                                 void* stream);
+
+/* a8 - mx.sym.BilinearSampler(data, grid) (SYM:307,321,469,572,679).
+ * data (N,C,Hi,Wi), grid (N,2,Ho,Wo) normalised to [-1,1], out (N,C,Ho,Wo); float32 NCHW. */
+LSFA_API int lsfa_bilinear_sampler_f32(const float* data, const float* grid, float* out, int N, int C,
+                              int Hi, int Wi, int Ho, int Wo, int req, void* stream);
+
+/* Parity probe: the integer/indexing math of a7+a8 on its own.  From flow (N,2,H,W) (or a
+ * grid when is_grid != 0) produce floor indices x0,y0 (int32) and top-left weights wx,wy
+ * (float32), each (N,H,W), for a key plane of Hi x Wi. */
+LSFA_API int lsfa_sampler_coords_f32(const float* flow_or_grid, int is_grid, int32_t* x0, int32_t* y0,
+                            float* wx, float* wy, int N, int H, int W, int Hi, int Wi,
+                            void* stream);
+
+/* The fused operator (a5-a15 in one pass).  The two suffixed names pin the layout the
+ * reference-side binding expects; lsfa_warp_scale_aggregate takes it from args->layout. */
+LSFA_API int    lsfa_warp_scale_aggregate(const LsfaAggArgs* args, void* stream);
+LSFA_API int    lsfa_warp_scale_aggregate_f32_nchw(const LsfaAggArgs* args, void* stream);
+LSFA_API int    lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream);
+LSFA_API size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args);
+/* kernels one call of the fused op enqueues for these args (for launch accounting) */
+LSFA_API int    lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args);
+
+/* a12 on its own: cosine logits of Fgfa_net (SYM:111-116,137-139).
+ * emb_* (N,E,H,W) f32 (layout NCHW_F32) or (N,H,W,E) (NHWC_*); logits (N,2,H,W) f32 with
+ * [n,0] = cos(emb_warp, emb_cur), [n,1] = cos(emb_cur, emb_cur). */
+LSFA_API int lsfa_cosine_logits(const void* emb_warp, const void* emb_cur, float* logits, int N, int E,
+                       int H, int W, int layout, void* stream);
+
+/* The reference graph op by op (one kernel per MXNet operator, each a full pass over
+ * HBM) - the "unfused" arm of the ablation; same results as the fused op in LOGITS mode
+ * with scale_map.  tmp: 5 feature-sized float32 buffers (N*C*H*W each), caller-owned. */
+LSFA_API int lsfa_unfused_chain_f32_nchw(const float* key, const float* flow, const float* scale_map,
+                                const float* cur, const float* logits, float* out, float* tmp,
+                                int N, int C, int H, int W, void* stream);
+LSFA_API int lsfa_unfused_chain_num_launches(void);
+
+/* a15 - ChooseFeat (operator_py/choose_feat.py:23-31) with the flag kept on the device:
+ * out[n] = eq_flag[n] ? conv_feat[n] : conv_feat_prop[n]; per_frame = C*H*W elements. */
+LSFA_API int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat_prop,
+                                  const uint8_t* eq_flag, float* out, int N, long long per_frame,
+                                  void* stream);
+
+/* layout helpers for the harness: NCHW f32 <-> NHWC {f32,bf16} */
+LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout,
+                      void* stream);
+LSFA_API int lsfa_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_layout,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSFA_OPS_H_ */

@@ -1,0 +1,335 @@
+// extern "C" entry points declared in include/lsfa_ops.h: argument validation, tiling
+// decisions and kernel launches.  No allocation, no synchronisation, no global mutable
+// state; errors are reported through a thread-local message like MXGetLastError().
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "lsfa_device.cuh"
+
+namespace lsfa {
+// aggregate_nchw.cu
+bool plan_plane_kernel(AggParams& P, size_t* smem_out);
+cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t st);
+cudaError_t launch_agg_nchw_generic(const AggParams& P, cudaStream_t st);
+cudaError_t launch_cosine_logits_nchw(const float* ew, const float* ec, float* logits, int N, int E,
+                                      int HW, cudaStream_t st);
+// aggregate_nhwc.cu
+cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st);
+cudaError_t launch_cosine_logits_nhwc(const void* ew, const void* ec, float* logits, int N, int E,
+                                      int HW, bool bf16, cudaStream_t st);
+// prep_ops.cu
+cudaError_t launch_mv_pool(const void* mv, bool is_i32, float* flow, int N, int h, int w, int H, int W,
+                           double scale, int mode, cudaStream_t st);
+cudaError_t launch_res_pool(const void* res, bool is_i32, float* out, int N, int h, int w, int H, int W,
+                            const double* means, double pixel_scale, int mode, cudaStream_t st);
+cudaError_t launch_mv_prepare(const int* in, float* out, int N, int h, int w, int oh, int ow,
+                              double im_scale, int negate, int hflip, cudaStream_t st);
+cudaError_t launch_grid_generator(const float* flow, float* grid, int N, int H, int W, float half_w,
+                                  float half_h, cudaStream_t st);
+cudaError_t launch_sampler_coords(const float* fg, int is_grid, int* x0, int* y0, float* wx, float* wy,
+                                  int N, int H, int W, float half_w, float half_h, float wk_m1,
+                                  float hk_m1, cudaStream_t st);
+cudaError_t launch_nchw_to_nhwc(const float* src, void* dst, int N, int C, int HW, bool bf16, cudaStream_t st);
+cudaError_t launch_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, bool bf16, cudaStream_t st);
+cudaError_t launch_unfused_chain(const float* key, const float* flow, const float* scale_map,
+                                 const float* cur, const float* logits, float* out, float* tmp, int N,
+                                 int C, int H, int W, float half_w, float half_h, cudaStream_t st);
+int unfused_chain_launches();
+cudaError_t launch_choose_feat(const float* a, const float* b, const unsigned char* flag, float* o,
+                               long long per_frame, long long total, cudaStream_t st);
+}  // namespace lsfa
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_result(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return LSFA_OK;
+  return fail(LSFA_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// MXNet evaluates (DType(dim) - 1.0) / 2.0 in double and stores it as a float32 scalar.
+inline float half_extent(int dim) { return (float)(((double)(float)dim - 1.0) / 2.0); }
+
+inline int ceil16(int v) { return (v + 15) / 16; }
+
+bool valid_req(int req) { return req >= LSFA_REQ_NULL && req <= LSFA_REQ_ADD; }
+
+// Validate an LsfaAggArgs and translate it; returns LSFA_OK or an error code.
+int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
+  if (!a) return fail(LSFA_E_BADARG, "args is NULL");
+  if (a->struct_bytes != (int32_t)sizeof(LsfaAggArgs))
+    return fail(LSFA_E_BADARG, "args->struct_bytes=%d, this library expects %zu (ABI %d)",
+                a->struct_bytes, sizeof(LsfaAggArgs), LSFA_ABI_VERSION);
+  if (a->layout < LSFA_LAYOUT_NCHW_F32 || a->layout > LSFA_LAYOUT_NHWC_BF16)
+    return fail(LSFA_E_BADARG, "unknown layout %d", a->layout);
+  if (a->N <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0)
+    return fail(LSFA_E_SHAPE, "non-positive dims N=%d C=%d H=%d W=%d", a->N, a->C, a->H, a->W);
+  if (!valid_req(a->req)) return fail(LSFA_E_BADARG, "unknown req %d", a->req);
+  const int Hk = a->key_h > 0 ? a->key_h : a->H, Wk = a->key_w > 0 ? a->key_w : a->W;
+  if ((a->key_h > 0) != (a->key_w > 0)) return fail(LSFA_E_SHAPE, "key_h/key_w must both be set or both 0");
+  if ((long long)a->H * a->W >= (1LL << 24) || (long long)Hk * Wk >= (1LL << 24))
+    return fail(LSFA_E_SHAPE, "planes of 2^24 pixels or more are not supported");
+  if (!a->key || !a->flow || !a->out) return fail(LSFA_E_BADARG, "key, flow and out are required");
+  if (a->flow_kind < LSFA_FLOW_PREPOOLED || a->flow_kind > LSFA_FLOW_GRID)
+    return fail(LSFA_E_BADARG, "unknown flow_kind %d", a->flow_kind);
+  if (a->flow_kind == LSFA_FLOW_RAW_I32 || a->flow_kind == LSFA_FLOW_RAW_F32) {
+    if (a->mv_h <= 0 || a->mv_w <= 0) return fail(LSFA_E_SHAPE, "raw MV needs mv_h, mv_w > 0");
+    if (ceil16(a->mv_h) != a->H || ceil16(a->mv_w) != a->W)
+      return fail(LSFA_E_SHAPE, "raw MV %dx%d pools to %dx%d, but H,W = %d,%d", a->mv_h, a->mv_w,
+                  ceil16(a->mv_h), ceil16(a->mv_w), a->H, a->W);
+    if (a->pool_mode != LSFA_POOL_CENTRE2X2 && a->pool_mode != LSFA_POOL_AVG16)
+      return fail(LSFA_E_BADARG, "unknown pool_mode %d", a->pool_mode);
+    if (!(a->im_scale > 0.0)) return fail(LSFA_E_BADARG, "im_scale must be > 0");
+  }
+  if (a->weight_mode < LSFA_W_NONE || a->weight_mode > LSFA_W_COSINE)
+    return fail(LSFA_E_BADARG, "unknown weight_mode %d", a->weight_mode);
+  if (a->weight_mode != LSFA_W_NONE && !a->cur) return fail(LSFA_E_BADARG, "cur is required for weight_mode %d", a->weight_mode);
+  if (a->weight_mode == LSFA_W_LOGITS && !a->logits) return fail(LSFA_E_BADARG, "logits is required for LSFA_W_LOGITS");
+  if (a->weight_mode == LSFA_W_COSINE) {
+    if (!a->emb_warp || !a->emb_cur) return fail(LSFA_E_BADARG, "emb_warp and emb_cur are required for LSFA_W_COSINE");
+    if (a->E <= 0) return fail(LSFA_E_SHAPE, "E must be > 0 for LSFA_W_COSINE");
+  }
+  if (a->bypass && a->weight_mode == LSFA_W_NONE)
+    return fail(LSFA_E_BADARG, "bypass needs cur (weight_mode != NONE)");
+  if (a->res && (!a->rnet_w || !a->rnet_b)) return fail(LSFA_E_BADARG, "res needs rnet_w and rnet_b");
+  if (a->key_index && a->num_keys <= 0) return fail(LSFA_E_BADARG, "key_index needs num_keys > 0");
+  if (a->layout != LSFA_LAYOUT_NCHW_F32) {
+    const int lanes = a->layout == LSFA_LAYOUT_NHWC_BF16 ? 8 : 4;
+    if (a->C % lanes) return fail(LSFA_E_ALIGN, "NHWC layout needs C %% %d == 0 (C=%d)", lanes, a->C);
+    if (a->weight_mode == LSFA_W_COSINE && a->E % lanes)
+      return fail(LSFA_E_ALIGN, "NHWC layout needs E %% %d == 0 (E=%d)", lanes, a->E);
+    const void* ptrs[] = {a->key, a->scale_map, a->cur, a->out, a->emb_warp, a->emb_cur};
+    for (const void* p : ptrs)
+      if (p && (reinterpret_cast<uintptr_t>(p) % 16))
+        return fail(LSFA_E_ALIGN, "NHWC tensors must be 16-byte aligned");
+  }
+
+  memset(&P, 0, sizeof(P));
+  P.N = a->N; P.C = a->C; P.H = a->H; P.W = a->W; P.HW = a->H * a->W;
+  P.Hk = Hk; P.Wk = Wk; P.HWk = Hk * Wk;
+  P.key = a->key; P.key_index = a->key_index;
+  P.flow_kind = a->flow_kind; P.flow = a->flow;
+  P.mv_h = a->mv_h; P.mv_w = a->mv_w;
+  P.mv_scale = a->im_scale * (1.0 / 16.0);      // image.py:224: scale = im_scale * rcnn_scale
+  P.pool_mode = a->pool_mode;
+  P.scale = a->scale_map; P.res = a->res; P.rnet_w = a->rnet_w; P.rnet_b = a->rnet_b;
+  P.cur = a->cur; P.mode = a->weight_mode; P.logits = a->logits;
+  P.emb_warp = a->emb_warp; P.emb_cur = a->emb_cur; P.E = a->E;
+  P.bypass = a->bypass; P.out = a->out; P.req_add = a->req == LSFA_REQ_ADD;
+  P.half_w = half_extent(a->W); P.half_h = half_extent(a->H);
+  P.wk_m1 = (float)(Wk - 1); P.hk_m1 = (float)(Hk - 1);
+  return LSFA_OK;
+}
+
+size_t cosine_ws_bytes(const LsfaAggArgs* a) {
+  if (!a || a->weight_mode != LSFA_W_COSINE || a->layout != LSFA_LAYOUT_NCHW_F32) return 0;
+  if (a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
+  return (size_t)a->N * 2 * a->H * a->W * sizeof(float);
+}
+
+int run_aggregate(const LsfaAggArgs* a, void* stream) {
+  lsfa::AggParams P;
+  int rc = build_params(a, P);
+  if (rc != LSFA_OK) return rc;
+  if (a->req == LSFA_REQ_NULL) return LSFA_OK;
+  cudaStream_t st = as_stream(stream);
+  if (a->layout == LSFA_LAYOUT_NCHW_F32) {
+    if (a->weight_mode == LSFA_W_COSINE) {
+      // NCHW embeddings are channel-planar: the per-pixel cosine needs its own pass over
+      // them (each byte still read once); its (N,2,H,W) result feeds the fused kernel.
+      const size_t need = cosine_ws_bytes(a);
+      if (!a->workspace || a->workspace_bytes < need)
+        return fail(LSFA_E_BADARG, "LSFA_W_COSINE in NCHW needs a workspace of %zu bytes", need);
+      if (reinterpret_cast<uintptr_t>(a->workspace) % 4) return fail(LSFA_E_ALIGN, "workspace must be 4-byte aligned");
+      float* lg = static_cast<float*>(a->workspace);
+      rc = cuda_result(lsfa::launch_cosine_logits_nchw(static_cast<const float*>(a->emb_warp),
+                                                       static_cast<const float*>(a->emb_cur), lg, a->N,
+                                                       a->E, P.HW, st),
+                       "cosine_logits_nchw launch");
+      if (rc != LSFA_OK) return rc;
+      P.logits = lg;
+    }
+    size_t smem = 0;
+    if (!a->force_generic && lsfa::plan_plane_kernel(P, &smem))
+      return cuda_result(lsfa::launch_agg_nchw_plane(P, smem, st), "agg_nchw_plane launch");
+    return cuda_result(lsfa::launch_agg_nchw_generic(P, st), "agg_nchw_generic launch");
+  }
+  return cuda_result(lsfa::launch_agg_nhwc(P, a->layout == LSFA_LAYOUT_NHWC_BF16, st), "agg_nhwc launch");
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsfa_version(void) { return LSFA_ABI_VERSION; }
+
+const char* lsfa_last_error(void) { return g_err; }
+
+static int mv_pool_common(const void* mv, bool is_i32, float* flow, int N, int h, int w, double im_scale,
+                          int mode, void* stream) {
+  if (!mv || !flow) return fail(LSFA_E_BADARG, "mv and flow are required");
+  if (N <= 0 || h <= 0 || w <= 0) return fail(LSFA_E_SHAPE, "non-positive dims N=%d h=%d w=%d", N, h, w);
+  if (mode != LSFA_POOL_CENTRE2X2 && mode != LSFA_POOL_AVG16) return fail(LSFA_E_BADARG, "unknown pool mode %d", mode);
+  if (!(im_scale > 0.0)) return fail(LSFA_E_BADARG, "im_scale must be > 0");
+  return cuda_result(lsfa::launch_mv_pool(mv, is_i32, flow, N, h, w, ceil16(h), ceil16(w),
+                                          im_scale * (1.0 / 16.0), mode, as_stream(stream)),
+                     "mv_pool launch");
+}
+int lsfa_mv_pool_i32(const int32_t* mv, float* flow, int N, int h, int w, double im_scale, int mode, void* stream) {
+  return mv_pool_common(mv, true, flow, N, h, w, im_scale, mode, stream);
+}
+int lsfa_mv_pool_f32(const float* mv, float* flow, int N, int h, int w, double im_scale, int mode, void* stream) {
+  return mv_pool_common(mv, false, flow, N, h, w, im_scale, mode, stream);
+}
+
+static int res_pool_common(const void* res, bool is_i32, float* out, int N, int h, int w, const double* means,
+                           double pixel_scale, int mode, void* stream) {
+  if (!res || !out) return fail(LSFA_E_BADARG, "res and out are required");
+  if (N <= 0 || h <= 0 || w <= 0) return fail(LSFA_E_SHAPE, "non-positive dims N=%d h=%d w=%d", N, h, w);
+  if (mode != LSFA_POOL_CENTRE2X2 && mode != LSFA_POOL_AVG16) return fail(LSFA_E_BADARG, "unknown pool mode %d", mode);
+  return cuda_result(lsfa::launch_res_pool(res, is_i32, out, N, h, w, ceil16(h), ceil16(w), means, pixel_scale,
+                                           mode, as_stream(stream)),
+                     "res_pool launch");
+}
+int lsfa_res_pool_i32(const int32_t* res, float* out, int N, int h, int w, const double* means,
+                      double pixel_scale, int mode, void* stream) {
+  return res_pool_common(res, true, out, N, h, w, means, pixel_scale, mode, stream);
+}
+int lsfa_res_pool_f32(const float* res, float* out, int N, int h, int w, const double* means,
+                      double pixel_scale, int mode, void* stream) {
+  return res_pool_common(res, false, out, N, h, w, means, pixel_scale, mode, stream);
+}
+
+int lsfa_mv_prepare_i32(const int32_t* mv_coviar, float* mv_out, int N, int h, int w, int oh, int ow,
+                        double im_scale, int negate, int hflip, void* stream) {
+  if (!mv_coviar || !mv_out) return fail(LSFA_E_BADARG, "mv_coviar and mv_out are required");
+  if (N <= 0 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  if (!(im_scale > 0.0)) return fail(LSFA_E_BADARG, "im_scale must be > 0");
+  if (im_scale == 1.0 && (oh != h || ow != w)) return fail(LSFA_E_SHAPE, "im_scale 1 needs oh,ow == h,w");
+  if (reinterpret_cast<uintptr_t>(mv_out) % 8) return fail(LSFA_E_ALIGN, "mv_out must be 8-byte aligned");
+  return cuda_result(lsfa::launch_mv_prepare(mv_coviar, mv_out, N, h, w, oh, ow, im_scale, negate, hflip,
+                                             as_stream(stream)),
+                     "mv_prepare launch");
+}
+
+int lsfa_grid_generator_warp_f32(const float* flow, float* grid, int N, int H, int W, void* stream) {
+  if (!flow || !grid) return fail(LSFA_E_BADARG, "flow and grid are required");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(LSFA_E_SHAPE, "non-positive dims N=%d H=%d W=%d", N, H, W);
+  return cuda_result(lsfa::launch_grid_generator(flow, grid, N, H, W, half_extent(W), half_extent(H),
+                                                 as_stream(stream)),
+                     "grid_generator launch");
+}
+
+int lsfa_bilinear_sampler_f32(const float* data, const float* grid, float* out, int N, int C, int Hi, int Wi,
+                              int Ho, int Wo, int req, void* stream) {
+  LsfaAggArgs a;
+  memset(&a, 0, sizeof(a));
+  a.struct_bytes = (int32_t)sizeof(a);
+  a.layout = LSFA_LAYOUT_NCHW_F32;
+  a.N = N; a.C = C; a.H = Ho; a.W = Wo; a.key_h = Hi; a.key_w = Wi;
+  a.key = data; a.flow_kind = LSFA_FLOW_GRID; a.flow = grid;
+  a.weight_mode = LSFA_W_NONE; a.out = out; a.req = req;
+  if (Hi <= 0 || Wi <= 0) return fail(LSFA_E_SHAPE, "non-positive input plane %dx%d", Hi, Wi);
+  return run_aggregate(&a, stream);
+}
+
+int lsfa_sampler_coords_f32(const float* flow_or_grid, int is_grid, int32_t* x0, int32_t* y0, float* wx,
+                            float* wy, int N, int H, int W, int Hi, int Wi, void* stream) {
+  if (!flow_or_grid || !x0 || !y0 || !wx || !wy) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || H <= 0 || W <= 0 || Hi <= 0 || Wi <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  return cuda_result(lsfa::launch_sampler_coords(flow_or_grid, is_grid, x0, y0, wx, wy, N, H, W, half_extent(W),
+                                                 half_extent(H), (float)(Wi - 1), (float)(Hi - 1),
+                                                 as_stream(stream)),
+                     "sampler_coords launch");
+}
+
+int lsfa_warp_scale_aggregate(const LsfaAggArgs* args, void* stream) { return run_aggregate(args, stream); }
+
+int lsfa_warp_scale_aggregate_f32_nchw(const LsfaAggArgs* args, void* stream) {
+  if (args && args->layout != LSFA_LAYOUT_NCHW_F32)
+    return fail(LSFA_E_BADARG, "lsfa_warp_scale_aggregate_f32_nchw called with layout %d", args->layout);
+  return run_aggregate(args, stream);
+}
+
+int lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream) {
+  if (args && args->layout != LSFA_LAYOUT_NHWC_BF16)
+    return fail(LSFA_E_BADARG, "lsfa_warp_scale_aggregate_bf16_nhwc called with layout %d", args->layout);
+  return run_aggregate(args, stream);
+}
+
+size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) { return cosine_ws_bytes(args); }
+
+int lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args) {
+  if (!args || args->req == LSFA_REQ_NULL) return 0;
+  return (args->weight_mode == LSFA_W_COSINE && args->layout == LSFA_LAYOUT_NCHW_F32) ? 2 : 1;
+}
+
+int lsfa_cosine_logits(const void* emb_warp, const void* emb_cur, float* logits, int N, int E, int H, int W,
+                       int layout, void* stream) {
+  if (!emb_warp || !emb_cur || !logits) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || E <= 0 || H <= 0 || W <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  if (layout == LSFA_LAYOUT_NCHW_F32)
+    return cuda_result(lsfa::launch_cosine_logits_nchw(static_cast<const float*>(emb_warp),
+                                                       static_cast<const float*>(emb_cur), logits, N, E, H * W,
+                                                       as_stream(stream)),
+                       "cosine_logits_nchw launch");
+  if (layout != LSFA_LAYOUT_NHWC_F32 && layout != LSFA_LAYOUT_NHWC_BF16) return fail(LSFA_E_BADARG, "unknown layout %d", layout);
+  const int lanes = layout == LSFA_LAYOUT_NHWC_BF16 ? 8 : 4;
+  if (E % lanes) return fail(LSFA_E_ALIGN, "NHWC layout needs E %% %d == 0", lanes);
+  if ((reinterpret_cast<uintptr_t>(emb_warp) % 16) || (reinterpret_cast<uintptr_t>(emb_cur) % 16))
+    return fail(LSFA_E_ALIGN, "NHWC tensors must be 16-byte aligned");
+  return cuda_result(lsfa::launch_cosine_logits_nhwc(emb_warp, emb_cur, logits, N, E, H * W,
+                                                     layout == LSFA_LAYOUT_NHWC_BF16, as_stream(stream)),
+                     "cosine_logits_nhwc launch");
+}
+
+int lsfa_unfused_chain_f32_nchw(const float* key, const float* flow, const float* scale_map, const float* cur,
+                                const float* logits, float* out, float* tmp, int N, int C, int H, int W,
+                                void* stream) {
+  if (!key || !flow || !scale_map || !cur || !logits || !out || !tmp) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || C < 4 || H <= 0 || W <= 0) return fail(LSFA_E_SHAPE, "need N,H,W > 0 and C >= 4");
+  return cuda_result(lsfa::launch_unfused_chain(key, flow, scale_map, cur, logits, out, tmp, N, C, H, W,
+                                                half_extent(W), half_extent(H), as_stream(stream)),
+                     "unfused chain launch");
+}
+int lsfa_unfused_chain_num_launches(void) { return lsfa::unfused_chain_launches(); }
+
+int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat_prop, const uint8_t* eq_flag, float* out,
+                         int N, long long per_frame, void* stream) {
+  if (!conv_feat || !conv_feat_prop || !eq_flag || !out) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || per_frame <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  return cuda_result(lsfa::launch_choose_feat(conv_feat, conv_feat_prop, eq_flag, out, per_frame,
+                                              (long long)N * per_frame, as_stream(stream)),
+                     "choose_feat launch");
+}
+
+int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout, void* stream) {
+  if (!src || !dst) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535) return fail(LSFA_E_SHAPE, "bad dims");
+  if (dst_layout != LSFA_LAYOUT_NHWC_F32 && dst_layout != LSFA_LAYOUT_NHWC_BF16) return fail(LSFA_E_BADARG, "dst_layout must be NHWC");
+  return cuda_result(lsfa::launch_nchw_to_nhwc(src, dst, N, C, H * W, dst_layout == LSFA_LAYOUT_NHWC_BF16,
+                                               as_stream(stream)),
+                     "nchw_to_nhwc launch");
+}
+int lsfa_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_layout, void* stream) {
+  if (!src || !dst) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535) return fail(LSFA_E_SHAPE, "bad dims");
+  if (src_layout != LSFA_LAYOUT_NHWC_F32 && src_layout != LSFA_LAYOUT_NHWC_BF16) return fail(LSFA_E_BADARG, "src_layout must be NHWC");
+  return cuda_result(lsfa::launch_nhwc_to_nchw(src, dst, N, C, H * W, src_layout == LSFA_LAYOUT_NHWC_BF16,
+                                               as_stream(stream)),
+                     "nhwc_to_nchw launch");
+}
+
+}  // extern "C"

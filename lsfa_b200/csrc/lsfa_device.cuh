@@ -1,0 +1,310 @@
+// Device-side building blocks shared by every kernel of the path (sm_100a only).
+//
+//  * exact_*   : the integer / indexing math of GridGenerator(warp) + BilinearSampler in
+//                the reference's float32 op order, written with round-to-nearest intrinsics
+//                so ptxas can neither contract to FMA nor re-associate (SURVEY.md section 7
+//                "fp32 coordinate round trip").
+//  * pool_*    : the stride-16 reduction of lib/utils/image.py:220-228 in float64.
+//  * mbar_* / bulk_g2s : mbarrier + cp.async.bulk (TMA bulk copy, SASS UBLKCP) wrappers.
+//  * ld/st helpers with cache hints for once-touched streams.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/lsfa_ops.h"
+
+namespace lsfa {
+
+// ---------------------------------------------------------------------------------------
+// Kernel-side view of LsfaAggArgs (plain values, passed by value as a __grid_constant__)
+// ---------------------------------------------------------------------------------------
+struct AggParams {
+  int N, C, H, W, HW;          // output dims
+  int Hk, Wk, HWk;             // key plane dims
+  const void* key;
+  const int* key_index;
+  int flow_kind;
+  const void* flow;
+  int mv_h, mv_w;
+  double mv_scale;             // im_scale * (1/16)
+  int pool_mode;
+  const void* scale;
+  const float* res;
+  const float* rnet_w;
+  const float* rnet_b;
+  const void* cur;
+  int mode;
+  const float* logits;
+  const void* emb_warp;
+  const void* emb_cur;
+  int E;
+  const unsigned char* bypass;
+  void* out;
+  int req_add;
+  float half_w, half_h;        // (W-1)/2, (H-1)/2 of the flow grid (GridGenerator)
+  float wk_m1, hk_m1;          // Wk-1, Hk-1 (BilinearSampler de-normalisation)
+  // tiling of the plane-resident kernel
+  int K;                       // channels per stage
+  int chunks;                  // C / K
+  int parts;                   // pixel parts per frame
+  int part_pix;                // pixels per part (multiple of block size)
+  int stages;
+  unsigned stage_bytes;
+  long long items;
+};
+
+// ---------------------------------------------------------------------------------------
+// a7: GridGenerator(warp)  -  grid = (flow + pos) / half - 1     (float32, add/div/sub)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_grid(float flow, float pos, float half) {
+  return __fsub_rn(__fdiv_rn(__fadd_rn(flow, pos), half), 1.0f);
+}
+
+// a8: real = (g + 1) * (dim - 1) / 2                              (float32, add/mul/div)
+__device__ __forceinline__ float exact_denorm(float g, float dim_m1) {
+  return __fdiv_rn(__fmul_rn(__fadd_rn(g, 1.0f), dim_m1), 2.0f);
+}
+
+// floor index with the same clamp the oracle applies to out-of-range / NaN coordinates
+__device__ __forceinline__ int exact_floor_index(float real) {
+  const float big = 16777216.0f;  // 2^24
+  float f = floorf(real);
+  if (!(f >= -big)) f = -big;     // also catches NaN
+  if (f > big) f = big;
+  return (int)f;
+}
+
+// top-left weight: w = float(1.0 - double(real - float(i0)))  (the literal 1.0 is a double)
+__device__ __forceinline__ float exact_tl_weight(float real, int i0) {
+  return (float)(1.0 - (double)__fsub_rn(real, (float)i0));
+}
+
+// One output pixel's sampling record: 4 tap weights (invalid taps zeroed) and a packed,
+// always-in-bounds address: bits[0,24) = ya*Wk+xa, bit 24 = xb-xa, bit 25 = (yb-ya) != 0.
+struct Taps {
+  float w00, w01, w10, w11;
+  unsigned packed;
+};
+
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int Hk, int Wk, float wk_m1,
+                                          float hk_m1) {
+  const float xr = exact_denorm(gx, wk_m1);
+  const float yr = exact_denorm(gy, hk_m1);
+  const int x0 = exact_floor_index(xr);
+  const int y0 = exact_floor_index(yr);
+  const float wx = exact_tl_weight(xr, x0);
+  const float wy = exact_tl_weight(yr, y0);
+  const double owx = 1.0 - (double)wx, owy = 1.0 - (double)wy;
+  const bool xl = (x0 >= 0) && (x0 <= Wk - 1);
+  const bool xh = (x0 + 1 >= 0) && (x0 + 1 <= Wk - 1);
+  const bool yl = (y0 >= 0) && (y0 <= Hk - 1);
+  const bool yh = (y0 + 1 >= 0) && (y0 + 1 <= Hk - 1);
+  Taps t;
+  t.w00 = (xl && yl) ? (float)((double)wy * (double)wx) : 0.0f;
+  t.w01 = (xh && yl) ? (float)((double)wy * owx) : 0.0f;
+  t.w10 = (xl && yh) ? (float)(owy * (double)wx) : 0.0f;
+  t.w11 = (xh && yh) ? (float)(owy * owx) : 0.0f;
+  const int xa = min(max(x0, 0), Wk - 1), xb = min(max(x0 + 1, 0), Wk - 1);
+  const int ya = min(max(y0, 0), Hk - 1), yb = min(max(y0 + 1, 0), Hk - 1);
+  t.packed = (unsigned)(ya * Wk + xa) | ((unsigned)(xb - xa) << 24) |
+             ((unsigned)(yb != ya) << 25);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// a3+a5+a6: stride-16 reduction of one (x|y) component of the raw MV image, float64.
+// centre2x2: ((p[7,7]+p[7,8]) + (p[8,7]+p[8,8])) * 0.25, zero padding beyond (h,w).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double raw_at(const T* __restrict__ img, int h, int w, int nch,
+                                         int y, int x, int ch) {
+  if (y >= h || x >= w) return 0.0;
+  return (double)__ldg(img + ((size_t)y * w + x) * nch + ch);
+}
+
+template <typename T>
+__device__ __forceinline__ double pool_cell(const T* __restrict__ img, int h, int w, int nch,
+                                            int cy, int cx, int ch, int mode) {
+  const int y0 = cy * 16, x0 = cx * 16;
+  if (mode == LSFA_POOL_CENTRE2X2) {
+    const double a = raw_at(img, h, w, nch, y0 + 7, x0 + 7, ch);
+    const double b = raw_at(img, h, w, nch, y0 + 7, x0 + 8, ch);
+    const double c = raw_at(img, h, w, nch, y0 + 8, x0 + 7, ch);
+    const double d = raw_at(img, h, w, nch, y0 + 8, x0 + 8, ch);
+    return __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d)), 0.25);
+  }
+  double acc = 0.0;
+  for (int r = 0; r < 16; ++r)
+    for (int q = 0; q < 16; ++q) acc = __dadd_rn(acc, raw_at(img, h, w, nch, y0 + r, x0 + q, ch));
+  return __dmul_rn(acc, 1.0 / 256.0);
+}
+
+// flow (feature cells) of output pixel (y,x) of frame n from whatever the caller supplied;
+// returns the normalised grid coordinates gx, gy.
+__device__ __forceinline__ void pixel_grid(const AggParams& P, int n, int y, int x, float& gx,
+                                           float& gy) {
+  const int p = y * P.W + x;
+  if (P.flow_kind == LSFA_FLOW_GRID) {
+    const float* g = (const float*)P.flow + (size_t)n * 2 * P.HW;
+    gx = __ldg(g + p);
+    gy = __ldg(g + P.HW + p);
+    return;
+  }
+  float fx, fy;
+  if (P.flow_kind == LSFA_FLOW_PREPOOLED) {
+    const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
+    fx = __ldg(f + p);
+    fy = __ldg(f + P.HW + p);
+  } else if (P.flow_kind == LSFA_FLOW_RAW_I32) {
+    const int* mv = (const int*)P.flow + (size_t)n * P.mv_h * P.mv_w * 2;
+    fx = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 0, P.pool_mode), P.mv_scale);
+    fy = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 1, P.pool_mode), P.mv_scale);
+  } else {
+    const float* mv = (const float*)P.flow + (size_t)n * P.mv_h * P.mv_w * 2;
+    fx = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 0, P.pool_mode), P.mv_scale);
+    fy = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 1, P.pool_mode), P.mv_scale);
+  }
+  gx = exact_grid(fx, (float)x, P.half_w);
+  gy = exact_grid(fy, (float)y, P.half_h);
+}
+
+// softmax over {l_warp, l_cur} as mx.sym.softmax: exp(x - max) / sum
+__device__ __forceinline__ void softmax2(float lw, float lc, float& ww, float& wc) {
+  const float m = fmaxf(lw, lc);
+  const float ew = expf(lw - m), ec = expf(lc - m);
+  const float s = ew + ec;
+  ww = ew / s;
+  wc = ec / s;
+}
+
+// per-pixel blend weights (ww on src0, wc on cur) for the non-cosine modes
+__device__ __forceinline__ void pixel_weights(const AggParams& P, int n, int p, float& ww,
+                                              float& wc) {
+  ww = 1.0f;
+  wc = 0.0f;
+  if (P.mode == LSFA_W_ADD) {
+    wc = 1.0f;
+  } else if (P.mode == LSFA_W_MEAN) {
+    ww = 0.5f;
+    wc = 0.5f;
+  } else if (P.mode == LSFA_W_LOGITS || P.mode == LSFA_W_COSINE) {
+    const float* l = P.logits + (size_t)n * 2 * P.HW;
+    softmax2(__ldg(l + p), __ldg(l + P.HW + p), ww, wc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (global -> shared), SASS: SYNCS / UBLKCP
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// once-touched streams: bypass L1 allocation on load, streaming store
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_cached_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream_v4(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// 16-byte vector <-> float lanes for the NHWC kernels
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int kLanes = 4;
+  __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int kLanes = 8;
+  __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
+    const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
+      f[2 * i] = __uint_as_float(u[i] << 16);
+      f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ uint4 pack(const float* f) {
+    unsigned u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      u[i] = *reinterpret_cast<unsigned*>(&h);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+  }
+};
+
+}  // namespace lsfa

@@ -1,0 +1,434 @@
+"""GPU parity tests proper: every call goes through the C ABI (lsfa_b200.ops -> ctypes ->
+liblsfa_b200.so) and is compared with the CPU oracle on the same seeded inputs.
+
+Gates: MV pooling and sampler indices bit-exact; fp32 features
+|a-b| <= 1e-5|b| + 1e-6 max|data|; bf16 variant rtol 2^-8 against the fp32 oracle evaluated
+on bf16-rounded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lsfa_oracle as O
+from tests._util import assert_close_bf16, assert_close_f32, make_case, oracle_fused
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x, cuda):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from lsfa_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------
+# integer / indexing math: bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w", [(608, 1008), (600, 1000), (75, 131), (16, 16), (7, 9), (1080, 1920)])
+@pytest.mark.parametrize("mode", ["centre2x2", "avg16"])
+@pytest.mark.parametrize("scale", [1.0, 0.78125, 1.0 / 0.6])
+def test_mv_pool_bit_exact(ops, cuda, h, w, mode, scale):
+    rng = np.random.default_rng(h * 31 + w)
+    n = 2
+    mv = rng.integers(-96, 97, size=(n, h, w, 2), dtype=np.int32)
+    want = O.mv_pool(mv, scale, O.POOL_CENTRE2X2 if mode == "centre2x2" else O.POOL_AVG16)
+    got = host(ops.mv_pool(dev(mv, cuda), scale, mode))
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    mvf = (mv.astype(np.float32) * np.float32(0.37)).astype(np.float32)   # non-integer field
+    want = O.mv_pool(mvf, scale, O.POOL_CENTRE2X2 if mode == "centre2x2" else O.POOL_AVG16)
+    got = host(ops.mv_pool(dev(mvf, cuda), scale, mode))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("h,w", [(600, 1000), (75, 131), (64, 64)])
+@pytest.mark.parametrize("means,ps", [((0.0, 0.0, 0.0), 1.0), ((103.06, 115.90, 123.15), 0.5)])
+def test_res_pool_bit_exact(ops, cuda, h, w, means, ps):
+    rng = np.random.default_rng(7)
+    res = rng.integers(-64, 65, size=(2, h, w, 3), dtype=np.int32)
+    for mode, om in (("centre2x2", O.POOL_CENTRE2X2), ("avg16", O.POOL_AVG16)):
+        want = O.res_pool(res, means, ps, om)
+        got = host(ops.res_pool(dev(res, cuda), means, ps, mode))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), mode
+
+
+def test_mv_pool_matches_reference_golden(ops, cuda, golden_ref):
+    """Fixtures produced by the reference's own transform_mv_res (tools/make_golden_from_reference.py)."""
+    g = golden_ref
+    for i in range(int(g["n_cases"])):
+        s = float(g["scale_%d" % i])
+        if s != 1.0:
+            continue   # stage-1 resize is covered by test_mv_prepare_*
+        got_mv, got_res = ops.transform_mv_res(dev(g["mv_in_%d" % i][None], cuda),
+                                               dev(g["res_in_%d" % i][None], cuda), s)
+        assert np.array_equal(host(got_mv), g["mv_out_%d" % i].astype(np.float32))
+        assert np.array_equal(host(got_res), g["res_out_%d" % i].astype(np.float32))
+    got_mv, got_res = ops.transform_mv_res(dev(g["mv_in_m"][None], cuda), dev(g["res_in_m"][None], cuda),
+                                           1.0, tuple(g["means_m"]), float(g["pscale_m"]))
+    assert np.array_equal(host(got_mv), g["mv_out_m"].astype(np.float32))
+    assert np.array_equal(host(got_res), g["res_out_m"].astype(np.float32))
+
+
+@pytest.fixture(scope="module")
+def golden_ref():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_transform_mv_res.npz"))
+
+
+@pytest.mark.parametrize("h,w,scale", [(90, 160, 0.78125), (72, 96, 1.25), (48, 80, 2.0), (96, 160, 1.0),
+                                       (117, 203, 600.0 / 117.0 / 4.0)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_mv_prepare_matches_oracle(ops, cuda, h, w, scale, flip):
+    rng = np.random.default_rng(3)
+    raw = rng.integers(-48, 49, size=(2, h, w, 2), dtype=np.int32)
+    got = host(ops.mv_prepare(dev(raw, cuda), scale, negate=True, flipped=flip))
+    want = np.stack([O.resize_linear_f32(O.mv_sign_flip(r, flip), scale) for r in raw])
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 38, 63), (1, 68, 120), (3, 7, 9), (1, 1, 5), (1, 5, 1)])
+def test_grid_generator_bit_exact(ops, cuda, N, H, W):
+    rng = np.random.default_rng(11)
+    flow = (rng.standard_normal((N, 2, H, W)) * 3).astype(np.float32)
+    flow[:, :, ::2, ::3] = np.round(flow[:, :, ::2, ::3])     # integer flows: the floor-flip cases
+    flow[0, :, 0, 0] = 0.0
+    with np.errstate(all="ignore"):
+        want = O.grid_generator_warp(flow)
+    got = host(ops.GridGenerator(dev(flow, cuda), transform_type="warp"))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("N,H,W,Hi,Wi", [(2, 38, 63, 38, 63), (1, 68, 120, 68, 120), (2, 9, 7, 12, 5)])
+def test_sampler_indices_bit_exact(ops, cuda, N, H, W, Hi, Wi):
+    rng = np.random.default_rng(5)
+    flow = (rng.standard_normal((N, 2, H, W)) * 4).astype(np.float32)
+    flow[:, :, ::2] = np.round(flow[:, :, ::2])
+    flow[0, :, :2] = 0.0
+    flow[0, 0, 3] = 1000.0      # far out of bounds
+    flow[0, 1, 3] = -1000.0
+    flow[-1, :, -1] = 0.5       # half-cell
+    if (H, W) == (Hi, Wi):
+        grid = O.grid_generator_warp(flow)
+        x0, y0, wx, wy = O.sampler_coords(grid, Hi, Wi)
+        gx0, gy0, gwx, gwy = ops.sampler_coords(dev(flow, cuda), (Hi, Wi), is_grid=False)
+        assert np.array_equal(host(gx0).astype(np.int32), x0)
+        assert np.array_equal(host(gy0).astype(np.int32), y0)
+        assert np.array_equal(host(gwx).view(np.uint32), wx.view(np.uint32))
+        assert np.array_equal(host(gwy).view(np.uint32), wy.view(np.uint32))
+    grid = (rng.random((N, 2, H, W)) * 2.4 - 1.2).astype(np.float32)
+    x0, y0, wx, wy = O.sampler_coords(grid, Hi, Wi)
+    gx0, gy0, gwx, gwy = ops.sampler_coords(dev(grid, cuda), (Hi, Wi), is_grid=True)
+    assert np.array_equal(gx0.cpu().numpy(), x0) and np.array_equal(gy0.cpu().numpy(), y0)
+    assert np.array_equal(host(gwx).view(np.uint32), wx.view(np.uint32))
+    assert np.array_equal(host(gwy).view(np.uint32), wy.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------
+# a8 BilinearSampler on its own (plane-resident and generic kernels, req write/add)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,C,Hi,Wi,Ho,Wo", [(2, 64, 38, 63, 38, 63), (1, 6, 68, 120, 68, 120),
+                                             (2, 5, 9, 7, 11, 13), (1, 3, 4, 4, 2, 2), (2, 8, 37, 63, 37, 63)])
+def test_bilinear_sampler(ops, cuda, N, C, Hi, Wi, Ho, Wo):
+    rng = np.random.default_rng(C)
+    data = O.synth_features(rng, (N, C, Hi, Wi))
+    grid = (rng.random((N, 2, Ho, Wo)) * 2.3 - 1.15).astype(np.float32)   # partly out of bounds
+    want = O.bilinear_sampler(data, grid)
+    got = ops.BilinearSampler(dev(data, cuda), dev(grid, cuda))
+    assert_close_f32(host(got), want, scale=np.abs(data).max(), what="write")
+    acc = ops.BilinearSampler(dev(data, cuda), dev(grid, cuda), out=got, req="add")
+    assert_close_f32(host(acc), 2 * want, scale=2 * np.abs(data).max(), what="add")
+
+
+def test_bilinear_sampler_matches_torch_grid_sample(ops, cuda):
+    """Second, independent implementation: align_corners=True, zeros padding."""
+    rng = np.random.default_rng(0)
+    data = O.synth_features(rng, (2, 32, 38, 63))
+    flow = O.mv_pool(O.synth_raw_mv(rng, 2, 600, 1000, 96))
+    grid = ops.GridGenerator(dev(flow, cuda))
+    got = host(ops.BilinearSampler(dev(data, cuda), grid))
+    ref = torch.nn.functional.grid_sample(torch.from_numpy(data), grid.cpu().permute(0, 2, 3, 1),
+                                          mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert np.abs(got - ref.numpy()).max() <= 2e-6 * np.abs(data).max()
+
+
+# ------------------------------------------------------------------------------------------
+# the fused operator: every weight mode x layout x kernel
+# ------------------------------------------------------------------------------------------
+MODES = [("none", O.W_NONE), ("add", O.W_ADD), ("mean", O.W_MEAN), ("logits", O.W_LOGITS), ("cosine", O.W_COSINE)]
+SHAPES = [(3, 64, 38, 63), (2, 8, 68, 120), (4, 16, 7, 9), (2, 32, 37, 63)]
+
+
+def run_fused(ops, cuda, d, mode_name, layout, use_scale=True, use_res=False, flow_kind="raw",
+              force_generic=False, req="write", out=None):
+    bf16 = layout == "nhwc_bf16"
+    nhwc = layout != "nchw"
+
+    def feat(x):
+        t = dev(x, cuda)
+        if not nhwc:
+            return t
+        return ops.to_nhwc(t, torch.bfloat16 if bf16 else torch.float32)
+
+    kw = dict(weight_mode=mode_name, layout=layout, force_generic=force_generic, req=req)
+    if mode_name != "none":
+        kw["cur"] = feat(d["cur"])
+    if use_scale:
+        kw["scale_map"] = feat(d["scale_map"])
+    if use_res:
+        kw.update(res=dev(d["res"], cuda), rnet_w=dev(d["rnet_w"], cuda), rnet_b=dev(d["rnet_b"], cuda))
+    if mode_name == "logits":
+        kw["logits"] = dev(d["logits"], cuda)
+    if mode_name == "cosine":
+        kw.update(emb_warp=feat(d["emb_warp"]), emb_cur=feat(d["emb_cur"]))
+    if "bypass" in d and mode_name != "none":
+        kw["bypass"] = dev(d["bypass"], cuda)
+    if "key_index" in d:
+        kw["key_index"] = dev(d["key_index"], cuda)
+    if flow_kind == "raw":
+        flow = dev(d["mv"], cuda)
+    elif flow_kind == "flow":
+        flow = dev(d["flow"], cuda)
+    else:
+        flow = ops.GridGenerator(dev(d["flow"], cuda))
+    if out is not None:
+        kw["out"] = out
+    res = ops.warp_scale_aggregate(feat(d["key"]), flow, flow_kind=flow_kind, **kw)
+    return ops.to_nchw(res) if nhwc else res
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode_name,mode", MODES)
+@pytest.mark.parametrize("layout,generic", [("nchw", False), ("nchw", True), ("nhwc_f32", False)])
+def test_fused_f32(ops, cuda, shape, mode_name, mode, layout, generic):
+    N, C, H, W = shape
+    d = make_case(hash((shape, mode)) % 1000, N, C, H, W, E=32 if mode == O.W_COSINE else 0,
+                  with_bypass=(mode != O.W_NONE and N >= 3))
+    want = oracle_fused(d, mode)
+    got = host(run_fused(ops, cuda, d, mode_name, layout, force_generic=generic))
+    scale = max(np.abs(d["key"]).max(), np.abs(d["cur"]).max())
+    assert_close_f32(got, want, scale=scale, what="%s %s %s" % (shape, mode_name, layout))
+
+
+@pytest.mark.parametrize("shape", SHAPES[:3])
+@pytest.mark.parametrize("mode_name,mode", MODES)
+def test_fused_bf16_nhwc(ops, cuda, shape, mode_name, mode):
+    N, C, H, W = shape
+    d = make_case(17 + mode, N, C, H, W, E=32 if mode == O.W_COSINE else 0, with_bypass=N >= 3 and mode != O.W_NONE)
+    for k in ("key", "cur", "scale_map", "emb_warp", "emb_cur"):
+        if k in d:
+            d[k] = O.bf16_round(d[k])           # oracle sees exactly what the kernel reads
+    want = oracle_fused(d, mode)
+    got = host(run_fused(ops, cuda, d, mode_name, "nhwc_bf16"))
+    assert_close_bf16(got, want, what="%s %s" % (shape, mode_name))
+
+
+@pytest.mark.parametrize("layout,generic", [("nchw", False), ("nchw", True), ("nhwc_f32", False), ("nhwc_bf16", False)])
+def test_cur_frame_path_as_shipped(ops, cuda, layout, generic):
+    """get_cur_test_symbol (SYM:570-586): warp(MV) + rnet_conv0(res) + small-net feature, no scale."""
+    d = make_case(101, 3, 64, 38, 63, with_res=True, raw="ragged")
+    if layout == "nhwc_bf16":
+        for k in ("key", "cur"):
+            d[k] = O.bf16_round(d[k])
+    want = O.cur_frame_path(d["key"], d["flow"], d["res"], d["rnet_w"], d["rnet_b"], d["cur"])
+    got = host(run_fused(ops, cuda, d, "add", layout, use_scale=False, use_res=True, force_generic=generic))
+    if layout == "nhwc_bf16":
+        assert_close_bf16(got, want, what=layout)
+    else:
+        assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what=layout)
+
+
+@pytest.mark.parametrize("flow_kind", ["raw", "flow", "grid"])
+def test_flow_sources_agree(ops, cuda, flow_kind):
+    """raw MV pooled in-kernel == pre-pooled flow == GridGenerator output fed as a grid: identical bits."""
+    d = make_case(5, 2, 16, 38, 63)
+    base = host(run_fused(ops, cuda, d, "logits", "nchw", flow_kind="raw"))
+    got = host(run_fused(ops, cuda, d, "logits", "nchw", flow_kind=flow_kind))
+    assert np.array_equal(base.view(np.uint32), got.view(np.uint32))
+
+
+def test_shared_key_feature_tile_as(ops, cuda):
+    """get_batch_test_symbol (SYM:675-680): one key feature, many frames (tile_as -> key_index)."""
+    d = make_case(9, 5, 32, 38, 63, shared_key=True)
+    want = O.batch_path(d["key"], d["flow"], d["scale_map"])
+    for layout in ("nchw", "nhwc_f32"):
+        got = host(run_fused(ops, cuda, d, "none", layout))
+        assert_close_f32(got, want, scale=np.abs(d["key"]).max(), what=layout)
+
+
+def test_req_add_and_null(ops, cuda):
+    d = make_case(21, 2, 16, 38, 63)
+    want = oracle_fused(d, O.W_LOGITS)
+    for layout, generic in (("nchw", False), ("nchw", True), ("nhwc_f32", False)):
+        first = run_fused(ops, cuda, d, "logits", layout, force_generic=generic)
+        if layout == "nchw":
+            acc = run_fused(ops, cuda, d, "logits", layout, force_generic=generic, req="add", out=first)
+            assert_close_f32(host(acc), 2 * want, scale=2 * np.abs(want).max(), what="add " + layout)
+            sentinel = torch.full_like(first, 7.0)
+            run_fused(ops, cuda, d, "logits", layout, req="null", out=sentinel)
+            assert float(host(sentinel).min()) == 7.0 == float(host(sentinel).max())
+
+
+def test_plane_generic_nhwc_identical_bits(ops, cuda):
+    """The three f32 kernels evaluate the same fmaf chain: results must agree bit for bit."""
+    d = make_case(33, 3, 64, 38, 63, with_bypass=True)
+    a = host(run_fused(ops, cuda, d, "logits", "nchw"))
+    b = host(run_fused(ops, cuda, d, "logits", "nchw", force_generic=True))
+    c = host(run_fused(ops, cuda, d, "logits", "nhwc_f32"))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+def test_unfused_chain_matches_fused(ops, cuda):
+    d = make_case(44, 2, 32, 38, 63)
+    want = oracle_fused(d, O.W_LOGITS)
+    got = host(ops.unfused_chain(dev(d["key"], cuda), dev(d["flow"], cuda), dev(d["scale_map"], cuda),
+                                 dev(d["cur"], cuda), dev(d["logits"], cuda)))
+    assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="unfused")
+
+
+def test_cosine_logits_op(ops, cuda):
+    rng = np.random.default_rng(2)
+    ew = rng.standard_normal((2, 2048, 9, 7), dtype=np.float32)
+    ec = rng.standard_normal((2, 2048, 9, 7), dtype=np.float32)
+    ec[:, :, 0, 0] = 0
+    want = np.concatenate([O.cosine_weight(ew, ec), O.cosine_weight(ec, ec)], axis=1)
+    got = host(ops.cosine_logits(dev(ew, cuda), dev(ec, cuda), "nchw"))
+    assert np.abs(got - want).max() < 2e-6
+    got = host(ops.cosine_logits(ops.to_nhwc(dev(ew, cuda)), ops.to_nhwc(dev(ec, cuda)), "nhwc_f32"))
+    assert np.abs(got - want).max() < 2e-6
+    assert got[0, 0, 0, 0] == 0.0 and got[0, 1, 0, 0] == 0.0     # eps path: 0/sqrt(1e-10)
+
+
+def test_choose_feat(ops, cuda):
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((4, 8, 5, 6), dtype=np.float32)
+    b = rng.standard_normal((4, 8, 5, 6), dtype=np.float32)
+    flag = np.array([1, 0, 0, 1], dtype=np.uint8)
+    got = host(ops.ChooseFeat(dev(a, cuda), dev(b, cuda), dev(flag, cuda)))
+    assert np.array_equal(got, O.choose_feat(a, b, flag))
+
+
+# ------------------------------------------------------------------------------------------
+# known-answer cases (SURVEY.md 8c i-ix)
+# ------------------------------------------------------------------------------------------
+def test_known_answers(ops, cuda):
+    rng = np.random.default_rng(0)
+    N, C, H, W = 2, 16, 38, 63
+    key = O.synth_features(rng, (N, C, H, W))
+    cur = O.synth_features(rng, (N, C, H, W))
+    ones = np.ones((N, C, H, W), np.float32)
+    K, Cu = dev(key, cuda), dev(cur, cuda)
+    # (i) zero flow: out == data up to the floor-flip epsilon
+    z = np.zeros((N, 2, H, W), np.float32)
+    got = host(ops.warp_scale_aggregate(K, dev(z, cuda)))
+    assert np.abs(got - key).max() <= 4e-6 * np.abs(key).max()
+    # (ii) integer flow = pure shift with zero padding
+    f = z.copy(); f[:, 0] = 2.0; f[:, 1] = -1.0
+    got = host(ops.warp_scale_aggregate(K, dev(f, cuda)))
+    want = np.zeros_like(key); want[:, :, 1:, :W - 2] = key[:, :, :H - 1, 2:]
+    assert np.abs(got - want).max() <= 4e-6 * np.abs(key).max()
+    # (iii) half-cell flow: exact 2-tap mean in x
+    f = z.copy(); f[:, 0] = 0.5
+    got = host(ops.warp_scale_aggregate(K, dev(f, cuda)))
+    want = np.zeros_like(key); want[..., :W - 1] = 0.5 * (key[..., :W - 1] + key[..., 1:]); want[..., W - 1] = 0.5 * key[..., W - 1]
+    assert np.abs(got - want).max() <= 4e-6 * np.abs(key).max()
+    # (iv) fully out of bounds -> zeros
+    f = z.copy(); f[:, 0] = 500.0
+    assert float(np.abs(host(ops.warp_scale_aggregate(K, dev(f, cuda)))).max()) == 0.0
+    # (v)+(vi) scale == 1, equal logits -> plain average
+    lg = np.zeros((N, 2, H, W), np.float32) + 0.3
+    f = (rng.standard_normal((N, 2, H, W)) * 2).astype(np.float32)
+    a = host(ops.warp_scale_aggregate(K, dev(f, cuda), cur=Cu, scale_map=dev(ones, cuda), weight_mode="logits", logits=dev(lg, cuda)))
+    b = host(ops.warp_scale_aggregate(K, dev(f, cuda), cur=Cu, weight_mode="mean"))
+    assert np.abs(a - b).max() <= 1e-6 * max(np.abs(key).max(), np.abs(cur).max())
+    # (viii) bypass -> cur, bit for bit
+    byp = np.array([1, 0], np.uint8)
+    a = host(ops.warp_scale_aggregate(K, dev(f, cuda), cur=Cu, weight_mode="mean", bypass=dev(byp, cuda)))
+    assert np.array_equal(a[0], cur[0]) and not np.array_equal(a[1], cur[1])
+    # (ix) centre-2x2 vs avg-16 pooling differ on a non-constant field
+    mv = rng.integers(-40, 41, size=(1, 64, 64, 2), dtype=np.int32)
+    p0 = host(ops.mv_pool(dev(mv, cuda), 1.0, "centre2x2")); p1 = host(ops.mv_pool(dev(mv, cuda), 1.0, "avg16"))
+    assert not np.array_equal(p0, p1)
+
+
+def test_fused_golden_fixture(ops, cuda):
+    """Committed golden vectors (tests/golden/fused_small.npz, made by tools/make_golden_fused.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fused_small.npz"))
+    d = {k: g[k] for k in g.files}
+    for mode_name, mode in MODES:
+        want = d["out_" + mode_name]
+        for layout in ("nchw", "nhwc_f32"):
+            got = host(run_fused(ops, cuda, d, mode_name, layout))
+            assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()),
+                             what="golden %s %s" % (mode_name, layout))
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json sizes: oracle on 2 frames + size-independent properties on the full batch
+# ------------------------------------------------------------------------------------------
+def test_full_size_config2_against_oracle(ops, cuda):
+    d = make_case(2026, 2, 1024, 38, 63, raw=True)
+    want = oracle_fused(d, O.W_LOGITS)
+    got = host(run_fused(ops, cuda, d, "logits", "nchw"))
+    assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="1024x38x63 nchw")
+    got = host(run_fused(ops, cuda, d, "logits", "nhwc_f32"))
+    assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="1024x38x63 nhwc")
+
+
+def test_full_size_config4_against_oracle(ops, cuda):
+    d = make_case(4, 1, 1024, 68, 120, raw=True, max_px=96)
+    want = oracle_fused(d, O.W_LOGITS)
+    got = host(run_fused(ops, cuda, d, "logits", "nchw"))
+    assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="1024x68x120")
+
+
+def test_full_batch_properties(ops, cuda):
+    """Config 2 at full batch (64 x 1024 x 38 x 63): linearity in the key feature, bypass identity,
+    and agreement of the plane-resident kernel with the generic one - no oracle needed."""
+    N, C, H, W = 64, 1024, 38, 63
+    g = torch.Generator(device=cuda).manual_seed(1)
+    key1 = torch.rand((N, C, H, W), device=cuda, generator=g)
+    key2 = torch.rand((N, C, H, W), device=cuda, generator=g)
+    cur = torch.rand((N, C, H, W), device=cuda, generator=g)
+    mv = dev(O.synth_raw_mv(np.random.default_rng(1), N, 600, 1000, 96), cuda)
+    logits = torch.randn((N, 2, H, W), device=cuda, generator=g)
+    w1 = ops.warp_scale_aggregate(key1, mv, flow_kind="raw")
+    w2 = ops.warp_scale_aggregate(key2, mv, flow_kind="raw")
+    w12 = ops.warp_scale_aggregate(key1 + key2, mv, flow_kind="raw")
+    assert float((w12 - (w1 + w2)).abs().max()) <= 1e-5
+    full = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits)
+    gen = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits,
+                                   force_generic=True)
+    assert torch.equal(full, gen)
+    # convexity: softmax weights sum to 1 -> out between min and max of the two sources
+    lo = torch.minimum(w1, cur) - 1e-5
+    hi = torch.maximum(w1, cur) + 1e-5
+    assert bool(((full >= lo) & (full <= hi)).all())
+    byp = torch.ones(N, dtype=torch.uint8, device=cuda)
+    same = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits, bypass=byp)
+    assert torch.equal(same, cur)
+
+
+def test_errors_are_loud(ops, cuda):
+    from lsfa_b200 import LsfaError
+    key = torch.zeros((1, 8, 4, 4), device=cuda)
+    flow = torch.zeros((1, 2, 4, 4), device=cuda)
+    with pytest.raises(LsfaError):
+        ops.warp_scale_aggregate(key, flow, weight_mode="logits", cur=key)      # logits missing
+    with pytest.raises(ValueError):
+        ops.warp_scale_aggregate(key.cpu(), flow)                               # no CPU path
+    with pytest.raises(NotImplementedError):
+        ops.GridGenerator(flow, transform_type="affine")
+    with pytest.raises(LsfaError):
+        ops.warp_scale_aggregate(torch.zeros((1, 4, 4, 6), device=cuda, dtype=torch.bfloat16), flow,
+                                 layout="nhwc_bf16")                            # C % 8 != 0

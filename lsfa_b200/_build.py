@@ -15,8 +15,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblsfa_b200.so")
-SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu"]
-HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"),
+SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu",
+           "plane_var0.cu", "plane_var1.cu", "plane_var2.cu", "plane_var3.cu", "plane_var4.cu"]
+HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"), os.path.join(CSRC, "aggregate_nchw_plane.cuh"),
+           os.path.join(CSRC, "plane_variant_impl.inc"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "lsfa_ops.h")]
 
 NVCC_FLAGS = [
@@ -25,7 +27,6 @@ NVCC_FLAGS = [
     "--fmad=true",            # value path may contract; the index path uses *_rn intrinsics
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v",
-    "-shared",
 ]
 
 
@@ -44,16 +45,34 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(nvcc: str, src: str, obj: str):
+    cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu to an object (in parallel: one nvcc per translation unit) and link."""
     if not force and not is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = find_nvcc()
+    jobs = [(os.path.join(CSRC, s), os.path.join(obj_dir, s[:-3] + ".o")) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda j: _compile_one(nvcc, *j), jobs))
+    log = "".join(r[1] for r in results)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [j[1] for j in jobs]
+    rc = max(r[0] for r in results)
+    if rc == 0:
+        proc = subprocess.run(link, capture_output=True, text=True)
+        log += " ".join(link) + "\n" + proc.stdout + proc.stderr
+        rc = proc.returncode
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
+        f.write(log)
+    if rc != 0:
         raise RuntimeError("nvcc failed:\n" + log[-8000:])
     if verbose:
         print(log)

@@ -1,0 +1,240 @@
+// agg_nchw_plane_kernel - "plane-resident gather": the headline kernel of the NCHW fp32 path.
+//
+// Replaces, in ONE pass over HBM, the operator chain of
+//   SYM:571-572 GridGenerator(warp) + BilinearSampler      (a7, a8)
+//   SYM:308/470/680  * scale_map                            (a9)
+//   SYM:66,576  + rnet_conv0(res_diff)                      (a10)
+//   SYM:236 / 104-108 / 144-147 / 315  aggregation          (a11-a14)
+//   operator_py/choose_feat.py:23-31  per-frame select      (a15)
+// and, when raw motion vectors are given, lib/utils/image.py:207-228 (a3,a5,a6).
+//
+// NCHW planes are small (38x63 fp32 = 9.6 KB), so K whole key planes are streamed into shared
+// memory with one TMA bulk copy (cp.async.bulk -> mbarrier, SASS UBLKCP) per stage of a ring
+// and the 4-tap gather runs against shared memory: HBM sees every key byte exactly once
+// whatever the motion magnitude.  scale_map / cur / out are pure coalesced streams.
+// The per-pixel sampling record (4 weights, 4 packed 16-bit tap offsets, blend weight) lives in
+// REGISTERS: each thread owns the same <= 8 pixels for every channel of a frame, so the MV
+// pooling, the exact fp32 grid round trip and the softmax run once per frame per CTA.
+// Persistent grid: one 512-thread CTA per SM walks a contiguous range of
+// (frame, channel-chunk, pixel-part) items.
+//
+// The per-element work is specialised at compile time (VAR) so the inner loop carries no
+// mode branches: ~22 instructions per element (4 LDS, 2 LDG, 1 STG, 6 FP, address adds).
+#pragma once
+#include "lsfa_device.cuh"
+
+namespace lsfa {
+
+constexpr int kPlaneThreads = 512;
+constexpr int kPlaneWarps = kPlaneThreads / 32;
+constexpr int kMaxStages = 8;
+constexpr int kBarrierBytes = 128;  // 2 * kMaxStages * 8
+
+// compile-time variants of the element arithmetic
+enum PlaneVariant : int {
+  kVarRuntime = 0,    // every flag read from AggParams (rare combinations, req = add)
+  kVarWarpOnly = 1,   // out = warp                       (BilinearSampler alone, SYM:572)
+  kVarScale = 2,      // out = warp * scale               (batch path, SYM:678-680)
+  kVarScaleCur = 3,   // out = wc*cur + ww*warp*scale     (key frame Nq/Fgfa/mean, SYM:468-476)
+  kVarResCur = 4,     // out = cur + warp + rnet(res)     (non-key frame as shipped, SYM:571-586)
+  kNumPlaneVariants = 5
+};
+
+template <int K, int PPT, int VAR>
+__global__ void __launch_bounds__(kPlaneThreads, 1)
+agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
+  constexpr bool RT = VAR == kVarRuntime;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + kMaxStages;
+  float* ring = reinterpret_cast<float*>(smem_raw + kBarrierBytes);
+  const unsigned stage_floats = P.stage_bytes / 4;
+  float* res_s = ring + (size_t)P.stages * stage_floats;  // [3][part_pix], thread-private slots
+
+  const int tid = threadIdx.x;
+  const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
+  const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
+  const long long items_per_frame = (long long)P.parts * P.chunks;
+  const float* __restrict__ scale = static_cast<const float*>(P.scale);
+  const float* __restrict__ cur = static_cast<const float*>(P.cur);
+  float* __restrict__ out = static_cast<float*>(P.out);
+  const bool has_scale = RT ? (scale != nullptr) : (VAR == kVarScale || VAR == kVarScaleCur);
+  const bool has_cur = RT ? (P.mode != LSFA_W_NONE) : (VAR == kVarScaleCur || VAR == kVarResCur);
+  const bool has_res = RT ? (P.res != nullptr) : (VAR == kVarResCur);
+  const bool req_add = RT ? (P.req_add != 0) : false;
+  const bool has_bypass = P.bypass != nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kPlaneWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // ---- producer state (meaningful in thread 0 only) ----
+  long long pit = i0;  // next item whose key planes have not been requested yet
+  int issued = 0;      // ring uses issued so far
+  auto try_issue_one = [&]() {
+    while (pit < i1 && has_bypass) {  // bypass frames never touch the key feature
+      const long long f = pit / items_per_frame;
+      if (!__ldg(P.bypass + f)) break;
+      pit = (f + 1) * items_per_frame;
+    }
+    if (pit >= i1) return;
+    const int n = (int)(pit / items_per_frame);
+    const int chunk = (int)((pit / P.parts) % P.chunks);
+    const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+    const float* src = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
+    const int s = issued % P.stages;
+    const int j = issued / P.stages;
+    if (j >= 1) mbar_wait(&empty[s], (unsigned)(j - 1) & 1u);
+    mbar_expect_tx(&full[s], P.stage_bytes);
+    bulk_g2s(ring + (size_t)s * stage_floats, src, P.stage_bytes, &full[s]);
+    ++issued;
+    ++pit;
+  };
+  if (tid == 0)
+    for (int s = 0; s < P.stages - 1; ++s) try_issue_one();
+
+  // ---- consumer state: the register-resident sampling records of this thread's pixels ----
+  float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
+  unsigned o_top[PPT], o_bot[PPT];   // byte offsets inside a plane: (i00 | i01 << 16), (i10 | i11 << 16)
+  int cur_n = -1, cur_part = -1;
+  int nv = 0;                        // how many of this thread's PPT pixel slots are inside the part
+  int used = 0;
+  const unsigned plane_bytes = (unsigned)P.HWk * 4u;
+
+  for (long long it = i0; it < i1; ++it) {
+    const int part = (int)(it % P.parts);
+    const int chunk = (int)((it / P.parts) % P.chunks);
+    const int n = (int)(it / items_per_frame);
+    const int pix0 = part * P.part_pix;
+    const bool byp = has_bypass && (__ldg(P.bypass + n) != 0);
+
+    if (n != cur_n || part != cur_part) {  // new frame (or pixel part): rebuild the records
+      cur_n = n;
+      cur_part = part;
+      const int pend = min(P.HW, pix0 + P.part_pix);
+      const int span = pend - pix0 - tid;
+      nv = span <= 0 ? 0 : min(PPT, (span + kPlaneThreads - 1) / kPlaneThreads);
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
+        o_top[j] = o_bot[j] = 0u;
+        if (j < nv && !byp) {
+          const int p = pix0 + tid + j * kPlaneThreads;
+          const int y = p / P.W, x = p - y * P.W;
+          float gx, gy;
+          pixel_grid(P, n, y, x, gx, gy);
+          PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
+          float bw, bc;
+          pixel_weights(P, n, p, bw, bc);
+          fold_blend(t, bw, bc);
+          w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+          wc[j] = t.wc; ww[j] = t.ww;
+          o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+          o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+          if (has_res) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              res_s[k * P.part_pix + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+          }
+        }
+      }
+    }
+
+    const int c0 = chunk * K;
+    const size_t e0 = ((size_t)n * P.C + c0) * P.HW + pix0 + tid;   // element of (k=0, j=0)
+
+    // once-touched streams first: they are in flight while we wait for the key planes
+    float sc[K][PPT], cu[K][PPT];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float* sp = scale + e0 + (size_t)k * P.HW;
+      const float* cp = cur + e0 + (size_t)k * P.HW;
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        sc[k][j] = 1.0f;
+        cu[k][j] = 0.0f;
+        if (j < nv) {
+          if (has_scale && !byp) sc[k][j] = ldg_stream(sp + j * kPlaneThreads);
+          if (has_cur) cu[k][j] = ldg_stream(cp + j * kPlaneThreads);
+        }
+      }
+    }
+
+    if (byp) {  // ChooseFeat: keep the current frame's own feature
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float* op = out + e0 + (size_t)k * P.HW;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (j < nv) __stcs(op + j * kPlaneThreads, req_add ? cu[k][j] + op[j * kPlaneThreads] : cu[k][j]);
+      }
+      continue;
+    }
+
+    if (tid == 0) try_issue_one();  // refills the stage consumed one item ago
+
+    const int s = used % P.stages;
+    mbar_wait(&full[s], (unsigned)(used / P.stages) & 1u);
+    const unsigned char* stage_s = smem_raw + kBarrierBytes + (size_t)s * P.stage_bytes;
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f, rb = 0.f;
+      if (has_res) {
+        rw0 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 0);
+        rw1 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 1);
+        rw2 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 2);
+        rb = __ldg(P.rnet_b + c0 + k);
+      }
+      const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
+      float* op = out + e0 + (size_t)k * P.HW;
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        if (j < nv) {
+          const float v00 = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+          const float v01 = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+          const float v10 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+          const float v11 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+          float v = w00[j] * v00;
+          v = fmaf(w01[j], v01, v);
+          v = fmaf(w10[j], v10, v);
+          v = fmaf(w11[j], v11, v);
+          if (has_scale) v *= sc[k][j];
+          if (has_res) {
+            const int q = tid + j * kPlaneThreads;
+            v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[P.part_pix + q], res_s[2 * P.part_pix + q]), v);
+          }
+          float o = has_cur ? fmaf(wc[j], cu[k][j], v) : v;
+          if (req_add) o += op[j * kPlaneThreads];   // kAddTo is the rare path: read late
+          __stcs(op + j * kPlaneThreads, o);
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    ++used;
+  }
+}
+
+// One translation unit per variant instantiates every (K, PPT) it serves; see plane_var*.cu.
+template <int VAR>
+cudaError_t launch_plane_variant(const AggParams& P, size_t smem, int grid, cudaStream_t st);
+
+#define LSFA_PLANE_FOREACH_KP(X) \
+  X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 8) X(4, 1) X(4, 2) X(4, 3) X(4, 5) X(4, 8)
+
+#define LSFA_PLANE_LAUNCH(VAR, KK, PP)                                                            \
+  if (P.K == KK && ppt == PP) {                                                                   \
+    auto kfn = agg_nchw_plane_kernel<KK, PP, VAR>;                                                \
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                               \
+    kfn<<<grid, kPlaneThreads, smem, st>>>(P);                                                    \
+    return cudaPeekAtLastError();                                                                 \
+  }
+
+}  // namespace lsfa

@@ -64,7 +64,7 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
     const int y = p / P.W, x = p - y * P.W;
     float gx, gy;
     pixel_grid(P, n, y, x, gx, gy);   // every lane computes the same record (warp-uniform)
-    const Taps t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
+    PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
     float ww, wc;
     if (P.mode == LSFA_W_COSINE) {
       const T* __restrict__ ew = static_cast<const T*>(P.emb_warp) + (size_t)q * P.E;
@@ -111,16 +111,15 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
       r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
     }
 
-    const int kn = P.key_index ? __ldg(P.key_index + n) : n;
-    const unsigned a = t.packed & 0xffffffu;
-    const unsigned dx = (t.packed >> 24) & 1u;
-    const unsigned dy = ((t.packed >> 25) & 1u) ? (unsigned)P.Wk : 0u;
-    const T* __restrict__ k00 = key + ((size_t)kn * P.HWk + a) * P.C;
-    const T* __restrict__ k01 = k00 + (size_t)dx * P.C;
-    const T* __restrict__ k10 = k00 + (size_t)dy * P.C;
-    const T* __restrict__ k11 = k10 + (size_t)dx * P.C;
     // taps outside the key plane are not read at all (the reference does not read them)
     const bool u00 = t.w00 != 0.f, u01 = t.w01 != 0.f, u10 = t.w10 != 0.f, u11 = t.w11 != 0.f;
+    fold_blend(t, ww, wc);
+    const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+    const T* __restrict__ kbase = key + (size_t)kn * P.HWk * P.C;
+    const T* __restrict__ k00 = kbase + (size_t)t.i00 * P.C;
+    const T* __restrict__ k01 = kbase + (size_t)t.i01 * P.C;
+    const T* __restrict__ k10 = kbase + (size_t)t.i10 * P.C;
+    const T* __restrict__ k11 = kbase + (size_t)t.i11 * P.C;
 
     for (int c = lane * L; c < P.C; c += CSTEP) {
       const uint4 z = make_uint4(0, 0, 0, 0);
@@ -139,22 +138,13 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
       V::unpack(vc, fc);
 #pragma unroll
       for (int i = 0; i < L; ++i) {
-        float v = t.w00 * f00[i];
-        v = fmaf(t.w01, f01[i], v);
-        v = fmaf(t.w10, f10[i], v);
-        v = fmaf(t.w11, f11[i], v);
+        float v = tap_chain(t, f00[i], f01[i], f10[i], f11[i]);
         if (scale) v *= fs[i];
         if (P.res) {
           const float* rw = P.rnet_w + (size_t)(c + i) * 3;
-          float r = __ldg(rw) * r0;
-          r = fmaf(__ldg(rw + 1), r1, r);
-          r = fmaf(__ldg(rw + 2), r2, r);
-          v += r + __ldg(P.rnet_b + c + i);
+          v = fmaf(t.ww, rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + c + i), r0, r1, r2), v);
         }
-        if (P.mode == LSFA_W_NONE) o[i] = v;
-        else if (P.mode == LSFA_W_ADD) o[i] = fc[i] + v;
-        else if (P.mode == LSFA_W_MEAN) o[i] = 0.5f * (v + fc[i]);
-        else o[i] = fmaf(wc, fc[i], ww * v);
+        o[i] = has_cur ? fmaf(t.wc, fc[i], v) : v;
       }
       if (P.req_add) {
         float b[L];

@@ -81,15 +81,17 @@ __device__ __forceinline__ float exact_tl_weight(float real, int i0) {
   return (float)(1.0 - (double)__fsub_rn(real, (float)i0));
 }
 
-// One output pixel's sampling record: 4 tap weights (invalid taps zeroed) and a packed,
-// always-in-bounds address: bits[0,24) = ya*Wk+xa, bit 24 = xb-xa, bit 25 = (yb-ya) != 0.
-struct Taps {
-  float w00, w01, w10, w11;
-  unsigned packed;
+// One output pixel's sampling record.  Tap weights have invalid (out-of-plane) taps zeroed and
+// are later pre-multiplied by the blend weight of the warped source (fold_blend); the four
+// element indices are clamped into the plane so every tap address is always readable.
+struct PixelRec {
+  float w00, w01, w10, w11;   // bilinear weights (x ww after fold_blend)
+  float ww, wc;               // blend weights of the warped source / the current feature
+  int i00, i01, i10, i11;     // element offsets inside one key plane
 };
 
-__device__ __forceinline__ Taps make_taps(float gx, float gy, int Hk, int Wk, float wk_m1,
-                                          float hk_m1) {
+__device__ __forceinline__ PixelRec make_taps(float gx, float gy, int Hk, int Wk, float wk_m1,
+                                              float hk_m1) {
   const float xr = exact_denorm(gx, wk_m1);
   const float yr = exact_denorm(gy, hk_m1);
   const int x0 = exact_floor_index(xr);
@@ -101,16 +103,51 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int Hk, int Wk, fl
   const bool xh = (x0 + 1 >= 0) && (x0 + 1 <= Wk - 1);
   const bool yl = (y0 >= 0) && (y0 <= Hk - 1);
   const bool yh = (y0 + 1 >= 0) && (y0 + 1 <= Hk - 1);
-  Taps t;
+  PixelRec t;
   t.w00 = (xl && yl) ? (float)((double)wy * (double)wx) : 0.0f;
   t.w01 = (xh && yl) ? (float)((double)wy * owx) : 0.0f;
   t.w10 = (xl && yh) ? (float)(owy * (double)wx) : 0.0f;
   t.w11 = (xh && yh) ? (float)(owy * owx) : 0.0f;
   const int xa = min(max(x0, 0), Wk - 1), xb = min(max(x0 + 1, 0), Wk - 1);
   const int ya = min(max(y0, 0), Hk - 1), yb = min(max(y0 + 1, 0), Hk - 1);
-  t.packed = (unsigned)(ya * Wk + xa) | ((unsigned)(xb - xa) << 24) |
-             ((unsigned)(yb != ya) << 25);
+  t.i00 = ya * Wk + xa;
+  t.i01 = ya * Wk + xb;
+  t.i10 = yb * Wk + xa;
+  t.i11 = yb * Wk + xb;
+  t.ww = 1.0f;
+  t.wc = 0.0f;
   return t;
+}
+
+// Fold the warped source's blend weight into the tap weights: one multiply per pixel instead
+// of one per element.  Exact for ww in {1, 0.5}; one extra rounding (<= 1 ulp) for softmax.
+__device__ __forceinline__ void fold_blend(PixelRec& t, float ww, float wc) {
+  t.ww = ww;
+  t.wc = wc;
+  t.w00 *= ww;
+  t.w01 *= ww;
+  t.w10 *= ww;
+  t.w11 *= ww;
+}
+
+// The per-element arithmetic shared by every fp32 kernel (so they agree bit for bit):
+//   v  = ww * bilinear(key)              (4-tap chain, weights pre-folded)
+//   v  = v * scale                       [a9]
+//   v += ww * (rw . res + rb)            [a10]
+//   o  = wc * cur + v                    [a11-a14]
+__device__ __forceinline__ float tap_chain(const PixelRec& t, float v00, float v01, float v10,
+                                           float v11) {
+  float v = t.w00 * v00;
+  v = fmaf(t.w01, v01, v);
+  v = fmaf(t.w10, v10, v);
+  return fmaf(t.w11, v11, v);
+}
+__device__ __forceinline__ float rnet_term(float rw0, float rw1, float rw2, float rb, float r0,
+                                           float r1, float r2) {
+  float r = rw0 * r0;
+  r = fmaf(rw1, r1, r);
+  r = fmaf(rw2, r2, r);
+  return r + rb;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -220,12 +257,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)   // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,

@@ -224,15 +224,9 @@ __global__ void unfused_sampler_kernel(const float* __restrict__ data, const flo
     const long long nc = i / HW;
     const int n = (int)(nc / C);
     const float gx = grid[((size_t)n * 2) * HW + p], gy = grid[((size_t)n * 2 + 1) * HW + p];
-    const Taps t = make_taps(gx, gy, H, W, (float)(W - 1), (float)(H - 1));
+    const PixelRec t = make_taps(gx, gy, H, W, (float)(W - 1), (float)(H - 1));
     const float* plane = data + (size_t)nc * HW;
-    const unsigned a = t.packed & 0xffffffu, dx = (t.packed >> 24) & 1u;
-    const unsigned dy = ((t.packed >> 25) & 1u) ? (unsigned)W : 0u;
-    float v = t.w00 * plane[a];
-    v = fmaf(t.w01, plane[a + dx], v);
-    v = fmaf(t.w10, plane[a + dy], v);
-    v = fmaf(t.w11, plane[a + dy + dx], v);
-    out[i] = v;
+    out[i] = tap_chain(t, plane[t.i00], plane[t.i01], plane[t.i10], plane[t.i11]);
   }
 }
 __global__ void ew_mul_kernel(const float* __restrict__ a, const float* __restrict__ b,

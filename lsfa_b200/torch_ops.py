@@ -1,0 +1,82 @@
+"""PyTorch custom-op harness (``torch.library``) over the C ABI.
+
+The role ``mx.operator.CustomOpProp`` plays in the reference (list_arguments / infer_shape /
+create_operator, operator_py/choose_feat.py:45-68): each op has a real implementation that
+enqueues our CUDA kernels and a ``register_fake`` that is the ``infer_shape``.  Registered under
+the ``lsfa::`` namespace:
+
+    lsfa::grid_generator_warp(flow) -> grid
+    lsfa::bilinear_sampler(data, grid) -> out
+    lsfa::mv_pool(mv, im_scale, mode) -> flow
+    lsfa::warp_scale_aggregate(key, flow, cur?, scale_map?, logits?, bypass?, weight_mode, flow_kind,
+                               im_scale, layout) -> out
+
+This is harness only - shapes, dtypes and dispatch; the arithmetic is in liblsfa_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+_MODES = ("none", "add", "mean", "logits", "cosine")
+_FLOWS = ("flow", "grid", "raw")
+_LAYOUTS = ("nchw", "nhwc_f32", "nhwc_bf16")
+
+
+@torch.library.custom_op("lsfa::grid_generator_warp", mutates_args=())
+def grid_generator_warp(flow: torch.Tensor) -> torch.Tensor:
+    return ops.GridGenerator(flow, transform_type="warp")
+
+
+@grid_generator_warp.register_fake
+def _(flow):
+    torch._check(flow.dim() == 4 and flow.shape[1] == 2, lambda: "flow must be (N,2,H,W)")
+    return torch.empty_like(flow)
+
+
+@torch.library.custom_op("lsfa::bilinear_sampler", mutates_args=())
+def bilinear_sampler(data: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+    return ops.BilinearSampler(data, grid)
+
+
+@bilinear_sampler.register_fake
+def _(data, grid):
+    torch._check(data.dim() == 4 and grid.dim() == 4 and grid.shape[1] == 2 and grid.shape[0] == data.shape[0],
+                 lambda: "data (N,C,Hi,Wi), grid (N,2,Ho,Wo)")
+    return data.new_empty((data.shape[0], data.shape[1], grid.shape[2], grid.shape[3]))
+
+
+@torch.library.custom_op("lsfa::mv_pool", mutates_args=())
+def mv_pool(mv: torch.Tensor, im_scale: float, mode: int) -> torch.Tensor:
+    return ops.mv_pool(mv, im_scale, mode)
+
+
+@mv_pool.register_fake
+def _(mv, im_scale, mode):
+    torch._check(mv.dim() == 4 and mv.shape[3] == 2, lambda: "mv must be (N,h,w,2)")
+    return mv.new_empty((mv.shape[0], 2, (mv.shape[1] + 15) // 16, (mv.shape[2] + 15) // 16), dtype=torch.float32)
+
+
+@torch.library.custom_op("lsfa::warp_scale_aggregate", mutates_args=())
+def warp_scale_aggregate(key: torch.Tensor, flow: torch.Tensor, cur: Optional[torch.Tensor],
+                         scale_map: Optional[torch.Tensor], logits: Optional[torch.Tensor],
+                         bypass: Optional[torch.Tensor], weight_mode: int, flow_kind: int,
+                         im_scale: float, layout: int) -> torch.Tensor:
+    return ops.warp_scale_aggregate(key, flow, cur=cur, scale_map=scale_map, logits=logits, bypass=bypass,
+                                    weight_mode=_MODES[weight_mode], flow_kind=_FLOWS[flow_kind],
+                                    im_scale=im_scale, layout=_LAYOUTS[layout])
+
+
+@warp_scale_aggregate.register_fake
+def _(key, flow, cur, scale_map, logits, bypass, weight_mode, flow_kind, im_scale, layout):
+    torch._check(key.dim() == 4 and flow.dim() == 4, lambda: "key and flow must be 4-D")
+    if flow_kind == 2:
+        n, h, w = flow.shape[0], (flow.shape[1] + 15) // 16, (flow.shape[2] + 15) // 16
+    else:
+        n, h, w = flow.shape[0], flow.shape[2], flow.shape[3]
+    if layout == 0:
+        return key.new_empty((n, key.shape[1], h, w))
+    return key.new_empty((n, h, w, key.shape[3]))

@@ -434,3 +434,32 @@ def test_errors_are_loud(ops, cuda):
     with pytest.raises(LsfaError):
         ops.warp_scale_aggregate(torch.zeros((1, 4, 4, 6), device=cuda, dtype=torch.bfloat16), flow,
                                  layout="nhwc_bf16")                            # C % 8 != 0
+
+
+def test_torch_library_ops_dispatch_to_cuda(ops, cuda):
+    """torch.ops.lsfa.* (the custom-op harness) run the same kernels as lsfa_b200.ops."""
+    import lsfa_b200.torch_ops  # noqa: F401
+    d = make_case(77, 2, 16, 38, 63)
+    t = lambda k: dev(d[k], cuda)  # noqa: E731
+    grid = torch.ops.lsfa.grid_generator_warp(t("flow"))
+    warped = torch.ops.lsfa.bilinear_sampler(t("key"), grid)
+    assert_close_f32(host(warped), O.warp(d["key"], d["flow"]), scale=np.abs(d["key"]).max(), what="torch.ops warp")
+    assert np.array_equal(host(torch.ops.lsfa.mv_pool(t("mv"), 1.0, 0)), d["flow"])
+    out = torch.ops.lsfa.warp_scale_aggregate(t("key"), t("mv"), t("cur"), t("scale_map"), t("logits"), None, 3, 2, 1.0, 0)
+    assert_close_f32(host(out), oracle_fused(d, O.W_LOGITS), scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()),
+                     what="torch.ops fused")
+
+
+def test_host_aggregator_pipeline(ops, cuda):
+    """The host-buffer front end (pinned in/out, chunked 3-stream pipeline) gives the same result."""
+    from lsfa_b200.host import HostAggregator
+    N, C, H, W = 7, 32, 38, 63
+    d = make_case(55, N, C, H, W)
+    host_in = {k: torch.from_numpy(d[k]).pin_memory() for k in ("key", "cur", "scale_map", "mv", "logits")}
+    out_host = torch.empty((N, C, H, W), dtype=torch.float32).pin_memory()
+    agg = HostAggregator(N, C, H, W, d["mv"].shape[1:3], cuda, chunk=2, depth=2)
+    for _ in range(3):      # slots are reused across calls
+        agg(host_in, out_host)
+    agg.synchronize()
+    assert_close_f32(out_host.numpy(), oracle_fused(d, O.W_LOGITS),
+                     scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="host pipeline")

@@ -221,7 +221,7 @@ def recorded_traffic(frames):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        per_frame = t["agg_nchw_plane_kernel"]["dram_bytes_per_frame"]
+        per_frame = t["agg_nchw_tma_kernel"]["dram_bytes_per_frame"]
         return float(per_frame) * frames
     except Exception:
         return None
@@ -286,7 +286,7 @@ def run_ours(args):
     launch_ms = ms_local / K
     achieved = alg_bytes / (launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(frames), "kernel": "agg_nchw_plane_kernel<2,5>",
+                "traffic": recorded_traffic(frames), "kernel": "agg_nchw_tma_kernel<K=2,PPT=5,ScaleCur>",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -388,6 +388,17 @@ def run_extras(dev, d, args):
         del tmp
     except Exception as e:
         out["unfused_fp32_nchw"] = {"error": repr(e)}
+    try:
+        # the LDG/STG plane-resident kernel (previous headline) on the same inputs
+        prep2 = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                                      weight_mode="logits", logits=d["logits"], force_generic=2)
+        s2 = torch.cuda.current_stream().cuda_stream
+        ms_p = time_launches(lambda: prep2.run(s2), 3, steps)
+        gb = algorithmic_bytes_v2(frames, 4) / (ms_p / 1e3) / 1e9
+        out["fused_fp32_nchw_plane_ldg"] = {"frames_per_s": frames / (ms_p / 1e3), "ms_per_step": ms_p,
+                                            "achieved_gbs": gb, "frac_of_measured_peak": gb / peak}
+    except Exception as e:
+        out["fused_fp32_nchw_plane_ldg"] = {"error": repr(e)}
     try:
         # config 3 shape: bf16 NHWC (batch limited by what is already resident: same frame count)
         nh = {k: ops.to_nhwc(d[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}

@@ -119,7 +119,8 @@ typedef struct LsfaAggArgs {
   void*   workspace;         /* lsfa_warp_scale_aggregate_workspace_bytes() bytes, or NULL if 0 */
   size_t  workspace_bytes;
 
-  int32_t force_generic;     /* debug/ablation: 1 = skip the plane-resident fast kernel */
+  int32_t force_generic;     /* kernel choice (NCHW): 0 auto, 1 generic gather, 2 plane-resident LDG/STG,
+                                3 all-TMA warp-specialised (error if it cannot serve the args) */
 } LsfaAggArgs;
 
 LSFA_API int         lsfa_version(void);

@@ -16,9 +16,11 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblsfa_b200.so")
 SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu",
-           "plane_var0.cu", "plane_var1.cu", "plane_var2.cu", "plane_var3.cu", "plane_var4.cu"]
+           "plane_var0.cu", "plane_var1.cu", "plane_var2.cu", "plane_var3.cu", "plane_var4.cu",
+           "tma_var1.cu", "tma_var2.cu", "tma_var3.cu", "tma_var4.cu"]
 HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"), os.path.join(CSRC, "aggregate_nchw_plane.cuh"),
-           os.path.join(CSRC, "plane_variant_impl.inc"),
+           os.path.join(CSRC, "plane_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma.cuh"),
+           os.path.join(CSRC, "tma_variant_impl.inc"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "lsfa_ops.h")]
 
 NVCC_FLAGS = [
@@ -46,7 +48,8 @@ def is_stale() -> bool:
 
 
 def _compile_one(nvcc: str, src: str, obj: str):
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src]
+    extra = os.environ.get("LSFA_NVCC_EXTRA", "").split()     # experiment knobs, e.g. -DLSFA_LD_POLICY=1
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, src]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     return proc.returncode, " ".join(cmd) + "\n" + proc.stdout + proc.stderr
 

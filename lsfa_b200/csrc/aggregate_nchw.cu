@@ -1,7 +1,7 @@
 // NCHW float32 path: host-side planning / dispatch of the plane-resident kernel
 // (aggregate_nchw_plane.cuh, instantiated per variant in plane_var*.cu), the generic gather
 // kernel for shapes the fast kernel does not take, and the cosine-logit pre-pass.
-#include "aggregate_nchw_plane.cuh"
+#include "aggregate_nchw_tma.cuh"
 
 namespace lsfa {
 
@@ -154,9 +154,12 @@ bool plan_plane_kernel(AggParams& P, size_t* smem_out) {
   if (K == 0) return false;
   if (reinterpret_cast<uintptr_t>(P.key) % 16) return false;
   if (((long long)P.C * P.HWk) % 4) return false;      // every frame's planes stay 16 B aligned
-  int ppt = 8;
+  // pixel slots per thread: 8 only for the lean variants at K=2 (register budget), else <= 5
+  const bool lean = !P.req_add && P.res == nullptr;
+  const int n_opt = (K == 2 && lean) ? 5 : 4;
   const int ppt_options[5] = {1, 2, 3, 5, 8};
-  for (int i = 4; i >= 0; --i)
+  int ppt = ppt_options[n_opt - 1];
+  for (int i = n_opt - 1; i >= 0; --i)
     if ((long long)ppt_options[i] * kPlaneThreads >= P.HW) ppt = ppt_options[i];
   P.K = K;
   P.chunks = P.C / K;
@@ -184,6 +187,74 @@ cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t 
     if (!has_scale && has_cur && has_res) return launch_plane_variant<kVarResCur>(P, smem, (int)grid, st);
   }
   return launch_plane_variant<kVarRuntime>(P, smem, (int)grid, st);
+}
+
+// ---- all-TMA kernel: planning and dispatch -------------------------------------------------
+static int variant_of(const AggParams& P) {
+  const bool has_scale = P.scale != nullptr, has_cur = P.mode != LSFA_W_NONE, has_res = P.res != nullptr;
+  if (P.req_add) return kVarRuntime;
+  if (!has_scale && !has_cur && !has_res) return kVarWarpOnly;
+  if (has_scale && !has_cur && !has_res) return kVarScale;
+  if (has_scale && has_cur && !has_res) return kVarScaleCur;
+  if (!has_scale && has_cur && has_res) return kVarResCur;
+  return kVarRuntime;
+}
+
+bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
+  const size_t kSmemMax = 227 * 1024;
+  const int var = variant_of(P);
+  if (var == kVarRuntime) return false;
+  if (P.HW > 8 * kTmaConsumers || P.HWk > 16383) return false;
+  const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
+  for (const void* q : ptrs)
+    if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
+  if (((long long)P.C * P.HW) % 4 || ((long long)P.C * P.HWk) % 4) return false;
+  const int ppt_options[5] = {1, 2, 3, 5, 8};
+  int ppt = 8;
+  for (int i = 4; i >= 0; --i)
+    if ((long long)ppt_options[i] * kTmaConsumers >= P.HW) ppt = ppt_options[i];
+  const bool has_scale = var == kVarScale || var == kVarScaleCur;
+  const size_t res_bytes = var == kVarResCur ? (size_t)3 * ppt * kTmaConsumers * 4 : 0;
+  const size_t pad = (((size_t)ppt * kTmaConsumers - P.HW) * 4 + 127) / 128 * 128;
+  const int prefer[2] = {2, 1};
+  for (int i = 0; i < 2; ++i) {
+    const int K = prefer[i];
+    if (P.C % K) continue;
+    if (((long long)K * P.HW) % 4 || ((long long)K * P.HWk) % 4) continue;   // 16-byte bulk copies
+    const unsigned key_bytes = (unsigned)((size_t)K * P.HWk * 4), io_bytes = (unsigned)((size_t)K * P.HW * 4);
+    const unsigned off_scale = (key_bytes + 127u) / 128u * 128u;
+    const unsigned off_io = has_scale ? off_scale + (io_bytes + 127u) / 128u * 128u : off_scale;
+    const unsigned stage_bytes = off_io + (io_bytes + 127u) / 128u * 128u;
+    long long stages = ((long long)kSmemMax - kBarrierBytes - (long long)res_bytes - (long long)pad) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 3 && !(i == 1 && stages >= 2)) continue;    // want >= 3 stages; K=1 may run with 2
+    P.K = K;
+    P.chunks = P.C / K;
+    P.parts = 1;
+    P.part_pix = ppt * kTmaConsumers;
+    P.stages = (int)stages;
+    P.stage_bytes = stage_bytes;
+    P.key_bytes = key_bytes;
+    P.io_bytes = io_bytes;
+    P.off_scale = off_scale;
+    P.off_io = off_io;
+    P.items = (long long)P.N * P.chunks;
+    *smem_out = kBarrierBytes + (size_t)P.stages * stage_bytes + res_bytes + pad;
+    return true;
+  }
+  return false;
+}
+
+cudaError_t launch_agg_nchw_tma(const AggParams& P, size_t smem, cudaStream_t st) {
+  long long grid = sm_count();
+  if (grid > P.items) grid = P.items;
+  switch (variant_of(P)) {
+    case kVarWarpOnly: return launch_tma_variant<kVarWarpOnly>(P, smem, (int)grid, st);
+    case kVarScale: return launch_tma_variant<kVarScale>(P, smem, (int)grid, st);
+    case kVarScaleCur: return launch_tma_variant<kVarScaleCur>(P, smem, (int)grid, st);
+    case kVarResCur: return launch_tma_variant<kVarResCur>(P, smem, (int)grid, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_agg_nchw_generic(const AggParams& P, cudaStream_t st) {

@@ -73,27 +73,50 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
   }
   __syncthreads();
 
+  // Item = (frame n, channel chunk, pixel part), walked incrementally: no divisions in the loop.
+  struct Cursor {
+    int n, chunk, part;
+    __device__ __forceinline__ void advance(int parts, int chunks) {
+      if (++part == parts) {
+        part = 0;
+        if (++chunk == chunks) {
+          chunk = 0;
+          ++n;
+        }
+      }
+    }
+  };
+  auto cursor_at = [&](long long it) {
+    Cursor c;
+    c.part = (int)(it % P.parts);
+    c.chunk = (int)((it / P.parts) % P.chunks);
+    c.n = (int)(it / items_per_frame);
+    return c;
+  };
+
   // ---- producer state (meaningful in thread 0 only) ----
-  long long pit = i0;  // next item whose key planes have not been requested yet
-  int issued = 0;      // ring uses issued so far
+  Cursor pc = cursor_at(i0);   // next item whose key planes have not been requested yet
+  long long pit = i0;
+  int ps = 0, pround = 0;      // ring slot / how many times the ring has wrapped
   auto try_issue_one = [&]() {
-    while (pit < i1 && has_bypass) {  // bypass frames never touch the key feature
-      const long long f = pit / items_per_frame;
-      if (!__ldg(P.bypass + f)) break;
-      pit = (f + 1) * items_per_frame;
+    while (pit < i1 && has_bypass && __ldg(P.bypass + pc.n)) {  // bypass frames never touch the key feature
+      pit += items_per_frame - ((long long)pc.chunk * P.parts + pc.part);
+      pc.part = 0;
+      pc.chunk = 0;
+      ++pc.n;
     }
     if (pit >= i1) return;
-    const int n = (int)(pit / items_per_frame);
-    const int chunk = (int)((pit / P.parts) % P.chunks);
-    const int kn = P.key_index ? __ldg(P.key_index + n) : n;
-    const float* src = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
-    const int s = issued % P.stages;
-    const int j = issued / P.stages;
-    if (j >= 1) mbar_wait(&empty[s], (unsigned)(j - 1) & 1u);
-    mbar_expect_tx(&full[s], P.stage_bytes);
-    bulk_g2s(ring + (size_t)s * stage_floats, src, P.stage_bytes, &full[s]);
-    ++issued;
+    const int kn = P.key_index ? __ldg(P.key_index + pc.n) : pc.n;
+    const float* src = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)pc.chunk * K) * P.HWk;
+    if (pround >= 1) mbar_wait(&empty[ps], (unsigned)(pround - 1) & 1u);
+    mbar_expect_tx(&full[ps], P.stage_bytes);
+    bulk_g2s(ring + (size_t)ps * stage_floats, src, P.stage_bytes, &full[ps]);
+    if (++ps == P.stages) {
+      ps = 0;
+      ++pround;
+    }
     ++pit;
+    pc.advance(P.parts, P.chunks);
   };
   if (tid == 0)
     for (int s = 0; s < P.stages - 1; ++s) try_issue_one();
@@ -101,15 +124,16 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
   // ---- consumer state: the register-resident sampling records of this thread's pixels ----
   float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
   unsigned o_top[PPT], o_bot[PPT];   // byte offsets inside a plane: (i00 | i01 << 16), (i10 | i11 << 16)
+  unsigned valid = 0;                // bit j: this thread's pixel slot j is inside the part
   int cur_n = -1, cur_part = -1;
-  int nv = 0;                        // how many of this thread's PPT pixel slots are inside the part
-  int used = 0;
+  int cs = 0;                        // ring slot of the next use
+  unsigned cphase = 0;               // its phase parity
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
+  const size_t chan_stride = (size_t)P.HW;
+  Cursor cc = cursor_at(i0);
 
-  for (long long it = i0; it < i1; ++it) {
-    const int part = (int)(it % P.parts);
-    const int chunk = (int)((it / P.parts) % P.chunks);
-    const int n = (int)(it / items_per_frame);
+  for (long long it = i0; it < i1; ++it, cc.advance(P.parts, P.chunks)) {
+    const int n = cc.n, part = cc.part;
     const int pix0 = part * P.part_pix;
     const bool byp = has_bypass && (__ldg(P.bypass + n) != 0);
 
@@ -117,70 +141,69 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
       cur_n = n;
       cur_part = part;
       const int pend = min(P.HW, pix0 + P.part_pix);
-      const int span = pend - pix0 - tid;
-      nv = span <= 0 ? 0 : min(PPT, (span + kPlaneThreads - 1) / kPlaneThreads);
+      valid = 0;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
-        o_top[j] = o_bot[j] = 0u;
-        if (j < nv && !byp) {
-          const int p = pix0 + tid + j * kPlaneThreads;
-          const int y = p / P.W, x = p - y * P.W;
-          float gx, gy;
-          pixel_grid(P, n, y, x, gx, gy);
-          PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
-          float bw, bc;
-          pixel_weights(P, n, p, bw, bc);
-          fold_blend(t, bw, bc);
-          w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
-          wc[j] = t.wc; ww[j] = t.ww;
-          o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
-          o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
-          if (has_res) {
+        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
+        const int p = pix0 + tid + j * kPlaneThreads;
+        if (p < pend) {
+          valid |= 1u << j;
+          if (!byp) {
+            const int y = p / P.W, x = p - y * P.W;
+            float gx, gy;
+            pixel_grid(P, n, y, x, gx, gy);
+            PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
+            float bw, bc;
+            pixel_weights(P, n, p, bw, bc);
+            fold_blend(t, bw, bc);
+            w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+            wc[j] = t.wc; ww[j] = t.ww;
+            o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+            o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+            if (has_res) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-              res_s[k * P.part_pix + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+              for (int k = 0; k < 3; ++k)
+                res_s[k * P.part_pix + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+            }
           }
         }
       }
     }
 
-    const int c0 = chunk * K;
-    const size_t e0 = ((size_t)n * P.C + c0) * P.HW + pix0 + tid;   // element of (k=0, j=0)
+    const int c0 = cc.chunk * K;
+    const size_t e0 = ((size_t)n * P.C + c0) * chan_stride + pix0 + tid;   // element of (k=0, j=0)
 
-    // once-touched streams first: they are in flight while we wait for the key planes
+    // once-touched streams first: they are in flight while we wait for the key planes.
+    // Predicated (not branched) so the unrolled loop stays straight-line code.
     float sc[K][PPT], cu[K][PPT];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const float* sp = scale + e0 + (size_t)k * P.HW;
-      const float* cp = cur + e0 + (size_t)k * P.HW;
+      const float* sp = scale + e0 + (size_t)k * chan_stride;
+      const float* cp = cur + e0 + (size_t)k * chan_stride;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
-        sc[k][j] = 1.0f;
-        cu[k][j] = 0.0f;
-        if (j < nv) {
-          if (has_scale && !byp) sc[k][j] = ldg_stream(sp + j * kPlaneThreads);
-          if (has_cur) cu[k][j] = ldg_stream(cp + j * kPlaneThreads);
-        }
+        const unsigned ok = (valid >> j) & 1u;
+        sc[k][j] = (has_scale && !byp) ? ldg_stream_if(sp + j * kPlaneThreads, ok) : 1.0f;
+        cu[k][j] = has_cur ? ldg_stream_if(cp + j * kPlaneThreads, ok) : 0.0f;
       }
     }
 
     if (byp) {  // ChooseFeat: keep the current frame's own feature
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        float* op = out + e0 + (size_t)k * P.HW;
+        float* op = out + e0 + (size_t)k * chan_stride;
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (j < nv) __stcs(op + j * kPlaneThreads, req_add ? cu[k][j] + op[j * kPlaneThreads] : cu[k][j]);
+          if ((valid >> j) & 1u) __stcs(op + j * kPlaneThreads, req_add ? cu[k][j] + op[j * kPlaneThreads] : cu[k][j]);
       }
       continue;
     }
 
     if (tid == 0) try_issue_one();  // refills the stage consumed one item ago
 
-    const int s = used % P.stages;
-    mbar_wait(&full[s], (unsigned)(used / P.stages) & 1u);
-    const unsigned char* stage_s = smem_raw + kBarrierBytes + (size_t)s * P.stage_bytes;
+    mbar_wait(&full[cs], cphase);
+    const unsigned char* stage_s = smem_raw + kBarrierBytes + (size_t)cs * P.stage_bytes;
 
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -192,32 +215,37 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
         rb = __ldg(P.rnet_b + c0 + k);
       }
       const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
-      float* op = out + e0 + (size_t)k * P.HW;
+      float* op = out + e0 + (size_t)k * chan_stride;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
-        if (j < nv) {
-          const float v00 = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
-          const float v01 = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
-          const float v10 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
-          const float v11 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
-          float v = w00[j] * v00;
-          v = fmaf(w01[j], v01, v);
-          v = fmaf(w10[j], v10, v);
-          v = fmaf(w11[j], v11, v);
-          if (has_scale) v *= sc[k][j];
-          if (has_res) {
-            const int q = tid + j * kPlaneThreads;
-            v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[P.part_pix + q], res_s[2 * P.part_pix + q]), v);
-          }
-          float o = has_cur ? fmaf(wc[j], cu[k][j], v) : v;
-          if (req_add) o += op[j * kPlaneThreads];   // kAddTo is the rare path: read late
-          __stcs(op + j * kPlaneThreads, o);
+        const float v00 = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+        const float v01 = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+        const float v10 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+        const float v11 = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+        float v = w00[j] * v00;
+        v = fmaf(w01[j], v01, v);
+        v = fmaf(w10[j], v10, v);
+        v = fmaf(w11[j], v11, v);
+        if (has_scale) v *= sc[k][j];
+        if (has_res) {
+          const int q = tid + j * kPlaneThreads;   // slots outside the part read slot-0-initialised garbage: never stored
+          v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[P.part_pix + q], res_s[2 * P.part_pix + q]), v);
+        }
+        float o = has_cur ? fmaf(wc[j], cu[k][j], v) : v;
+        const unsigned ok = (valid >> j) & 1u;
+        if (req_add) {
+          if (ok) __stcs(op + j * kPlaneThreads, o + op[j * kPlaneThreads]);   // kAddTo: the rare path
+        } else {
+          stg_stream_if(op + j * kPlaneThreads, o, ok);
         }
       }
     }
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-    ++used;
+    if ((tid & 31) == 0) mbar_arrive(&empty[cs]);
+    if (++cs == P.stages) {
+      cs = 0;
+      cphase ^= 1u;
+    }
   }
 }
 

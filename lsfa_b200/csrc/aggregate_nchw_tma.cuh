@@ -1,0 +1,245 @@
+// agg_nchw_tma_kernel - the all-TMA, warp-specialised form of the plane-resident gather.
+//
+// Same operator chain as agg_nchw_plane_kernel (SYM:571-576, 308/470/680, 236, 104-108,
+// 144-147, 315; choose_feat.py:23-31) but NO thread ever touches global memory for the
+// feature streams: a dedicated producer warp moves every byte with bulk async copies
+//     HBM --cp.async.bulk (TMA, mbarrier complete_tx)--> SMEM stage {key planes, scale, cur}
+//     SMEM stage {out, written in place over cur} --cp.async.bulk (TMA store, bulk_group)--> HBM
+// and 16 consumer warps do shared-memory-only work (4 gather taps + 2 streaming loads + 1
+// store per element).  Why it beats the LDG/STG form: NCHW planes of 38x63 floats start at
+// 8-byte phases inside 32-byte DRAM sectors, so every warp-wide 128-byte global access
+// straddles a sector that its neighbour warp touches again; with evict-first streams the
+// second touch often misses L2 (+14% DRAM reads measured).  TMA reads each 19 KB chunk once.
+//
+// Pipeline (S stages, S >= 2):  full[s]  : producer -> consumers   (TMA bytes landed)
+//                               done[s]  : consumers -> producer   (stage computed, out in smem)
+//   producer: wait done[c] -> TMA-store stage c -> wait_group.read -> TMA-load item c+S into it
+#pragma once
+#include "aggregate_nchw_plane.cuh"
+
+namespace lsfa {
+
+constexpr int kTmaConsumers = 480;   // 15 warps: 480 x 5 = 2400 slots for 38x63 = 2394 pixels
+constexpr int kTmaConsumerWarps = kTmaConsumers / 32;
+constexpr int kTmaThreads = kTmaConsumers + 32;   // + one producer warp
+
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int K, int PPT, int VAR>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
+  static_assert(VAR != kVarRuntime, "the TMA kernel is only built for the compile-time variants");
+  constexpr bool has_scale = VAR == kVarScale || VAR == kVarScaleCur;
+  constexpr bool has_cur = VAR == kVarScaleCur || VAR == kVarResCur;
+  constexpr bool has_res = VAR == kVarResCur;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* done = full + kMaxStages;
+  unsigned char* ring = smem_raw + kBarrierBytes;
+  float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);  // [3][PPT*512]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
+  const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
+  const bool has_bypass = P.bypass != nullptr;
+  const size_t chunk_elems = (size_t)K * P.HW;
+
+  if (tid == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&done[s], kTmaConsumerWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // item = (frame n, channel chunk); pixel parts are not used by this kernel (plan: parts == 1)
+  auto frame_of = [&](long long it, int& n, int& chunk) {
+    n = (int)(it / P.chunks);
+    chunk = (int)(it - (long long)n * P.chunks);
+  };
+
+  if (warp == kTmaConsumerWarps) {
+    // =========================== producer warp (one elected lane) ===========================
+    if ((tid & 31) == 0) {
+      int ln, lchunk;          // load cursor
+      frame_of(i0, ln, lchunk);
+      long long lit = i0;
+      auto issue_loads = [&](int s) {
+        const bool byp = has_bypass && __ldg(P.bypass + ln) != 0;
+        unsigned char* st = ring + (size_t)s * P.stage_bytes;
+        const size_t e0 = ((size_t)ln * P.C + (size_t)lchunk * K) * P.HW;
+        uint32_t bytes = has_cur ? P.io_bytes : 0u;
+        if (!byp) bytes += P.key_bytes + (has_scale ? P.io_bytes : 0u);
+        mbar_expect_tx(&full[s], bytes);
+        if (!byp) {
+          const int kn = P.key_index ? __ldg(P.key_index + ln) : ln;
+          const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)lchunk * K) * P.HWk;
+          bulk_g2s(st, ksrc, P.key_bytes, &full[s]);
+          if (has_scale) bulk_g2s(st + P.off_scale, static_cast<const float*>(P.scale) + e0, P.io_bytes, &full[s]);
+        }
+        if (has_cur) bulk_g2s(st + P.off_io, static_cast<const float*>(P.cur) + e0, P.io_bytes, &full[s]);
+        ++lit;
+        if (++lchunk == P.chunks) {
+          lchunk = 0;
+          ++ln;
+        }
+      };
+      for (int s = 0; s < P.stages && lit < i1; ++s) issue_loads(s);
+
+      int sn, schunk;          // store cursor
+      frame_of(i0, sn, schunk);
+      int s = 0;
+      unsigned ph = 0;
+      for (long long c = i0; c < i1; ++c) {
+        mbar_wait(&done[s], ph);                       // consumers finished this stage; out is in smem
+        unsigned char* st = ring + (size_t)s * P.stage_bytes;
+        float* dst = static_cast<float*>(P.out) + ((size_t)sn * P.C + (size_t)schunk * K) * P.HW;
+        bulk_s2g(dst, st + P.off_io, P.io_bytes);
+        bulk_commit();
+        if (lit < i1) {
+          bulk_wait_read_all();                        // the store has drained the stage: safe to refill
+          issue_loads(s);
+        }
+        if (++schunk == P.chunks) {
+          schunk = 0;
+          ++sn;
+        }
+        if (++s == P.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      bulk_wait_all();                                 // every store is complete before the CTA exits
+    }
+    return;
+  }
+
+  // ================================= consumer warps ==========================================
+  float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
+  unsigned o_top[PPT], o_bot[PPT];
+  unsigned valid = 0;
+  int cur_n = -1;
+  int n, chunk;
+  frame_of(i0, n, chunk);
+  int s = 0;
+  unsigned ph = 0;
+  const unsigned plane_bytes = (unsigned)P.HWk * 4u;
+  const unsigned io_plane_bytes = (unsigned)P.HW * 4u;
+  (void)ww;
+
+  for (long long it = i0; it < i1; ++it) {
+    const bool byp = has_bypass && (__ldg(P.bypass + n) != 0);
+    if (n != cur_n) {  // new frame: rebuild this thread's sampling records
+      cur_n = n;
+      valid = 0;
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
+        o_top[j] = o_bot[j] = 0u;
+        const int p = tid + j * kTmaConsumers;
+        if (p < P.HW) {
+          valid |= 1u << j;
+          if (!byp) {
+            const int y = p / P.W, x = p - y * P.W;
+            float gx, gy;
+            pixel_grid(P, n, y, x, gx, gy);
+            PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
+            float bw, bc;
+            pixel_weights(P, n, p, bw, bc);
+            fold_blend(t, bw, bc);
+            w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+            wc[j] = t.wc; ww[j] = t.ww;
+            o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+            o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+            if (has_res) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                res_s[k * (PPT * kTmaConsumers) + p] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+            }
+          }
+        }
+      }
+    }
+
+    mbar_wait(&full[s], ph);
+    if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
+      unsigned char* stage_s = ring + (size_t)s * P.stage_bytes;
+      const int c0 = chunk * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f, rb = 0.f;
+        if (has_res) {
+          rw0 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 0);
+          rw1 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 1);
+          rw2 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 2);
+          rb = __ldg(P.rnet_b + c0 + k);
+        }
+        const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
+        const float* sc_s = reinterpret_cast<const float*>(stage_s + P.off_scale + (size_t)k * io_plane_bytes) + tid;
+        float* io_s = reinterpret_cast<float*>(stage_s + P.off_io + (size_t)k * io_plane_bytes) + tid;
+        float v00[PPT], v01[PPT], v10[PPT], v11[PPT], sc[PPT], cu[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {   // all shared-memory reads of the plane first ...
+          v00[j] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+          v01[j] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+          v10[j] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+          v11[j] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+          sc[j] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;   // slots past the plane read the tail pad
+          cu[j] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {   // ... then the arithmetic and the in-place stores
+          float v = w00[j] * v00[j];
+          v = fmaf(w01[j], v01[j], v);
+          v = fmaf(w10[j], v10[j], v);
+          v = fmaf(w11[j], v11[j], v);
+          if (has_scale) v *= sc[j];
+          if (has_res) {
+            const int q = tid + j * kTmaConsumers;
+            v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
+                                      res_s[2 * PPT * kTmaConsumers + q]), v);
+          }
+          const float o = has_cur ? fmaf(wc[j], cu[j], v) : v;
+          if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&done[s]);
+    if (++s == P.stages) {
+      s = 0;
+      ph ^= 1u;
+    }
+    if (++chunk == P.chunks) {
+      chunk = 0;
+      ++n;
+    }
+  }
+}
+
+template <int VAR>
+cudaError_t launch_tma_variant(const AggParams& P, size_t smem, int grid, cudaStream_t st);
+
+#define LSFA_TMA_FOREACH_KP(X) X(1, 1) X(1, 2) X(1, 3) X(1, 5) X(1, 8) X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 8)
+
+#define LSFA_TMA_LAUNCH(VAR, KK, PP)                                                              \
+  if (P.K == KK && ppt == PP) {                                                                   \
+    auto kfn = agg_nchw_tma_kernel<KK, PP, VAR>;                                                  \
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                               \
+    kfn<<<grid, kTmaThreads, smem, st>>>(P);                                                      \
+    return cudaPeekAtLastError();                                                                 \
+  }
+
+}  // namespace lsfa

@@ -10,6 +10,8 @@
 namespace lsfa {
 // aggregate_nchw.cu
 bool plan_plane_kernel(AggParams& P, size_t* smem_out);
+bool plan_tma_kernel(AggParams& P, size_t* smem_out);
+cudaError_t launch_agg_nchw_tma(const AggParams& P, size_t smem, cudaStream_t st);
 cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t st);
 cudaError_t launch_agg_nchw_generic(const AggParams& P, cudaStream_t st);
 cudaError_t launch_cosine_logits_nchw(const float* ew, const float* ec, float* logits, int N, int E,
@@ -162,7 +164,12 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
       P.logits = lg;
     }
     size_t smem = 0;
-    if (!a->force_generic && lsfa::plan_plane_kernel(P, &smem))
+    // kernel choice: 0 auto (all-TMA, then plane-resident LDG/STG, then generic); the other
+    // values pin one kernel for tests and ablations
+    if ((a->force_generic == 0 || a->force_generic == 3) && lsfa::plan_tma_kernel(P, &smem))
+      return cuda_result(lsfa::launch_agg_nchw_tma(P, smem, st), "agg_nchw_tma launch");
+    if (a->force_generic == 3) return fail(LSFA_E_UNSUPPORTED, "the all-TMA kernel cannot serve these arguments");
+    if (a->force_generic != 1 && lsfa::plan_plane_kernel(P, &smem))
       return cuda_result(lsfa::launch_agg_nchw_plane(P, smem, st), "agg_nchw_plane launch");
     return cuda_result(lsfa::launch_agg_nchw_generic(P, st), "agg_nchw_generic launch");
   }

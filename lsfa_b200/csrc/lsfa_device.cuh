@@ -53,6 +53,8 @@ struct AggParams {
   int stages;
   unsigned stage_bytes;
   long long items;
+  // stage layout of the all-TMA kernel: [key planes | scale chunk | cur/out chunk]
+  unsigned key_bytes, io_bytes, off_scale, off_io;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -281,6 +283,38 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+// Cache policy of the once-touched streams (compile-time experiment knob):
+//   0: ld.global.nc.L1::no_allocate + st.global.cs   1: ld.global.nc (L1 allocate) + st.global.cs  <- default:
+//      measured 5373 vs 4910 GB/s; the sector a warp shares with its neighbour then hits in L1
+//   2: ld.global.nc.L1::no_allocate + st.global (write-back)   3: ld.global.nc + st.global
+#ifndef LSFA_LD_POLICY
+#define LSFA_LD_POLICY 1
+#endif
+#if (LSFA_LD_POLICY & 1)
+#define LSFA_LD_STREAM "ld.global.nc.f32"
+#else
+#define LSFA_LD_STREAM "ld.global.nc.L1::no_allocate.f32"
+#endif
+#if (LSFA_LD_POLICY & 2)
+#define LSFA_ST_STREAM "st.global.f32"
+#else
+#define LSFA_ST_STREAM "st.global.cs.f32"
+#endif
+// predicated forms: no branch, no load/store when ok == 0 (the result is then undefined)
+__device__ __forceinline__ float ldg_stream_if(const float* p, unsigned ok) {
+  float v;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n mov.f32 %0, 0f00000000;\n"
+      "@q " LSFA_LD_STREAM " %0, [%1];\n}"
+      : "=f"(v)
+      : "l"(p), "r"(ok));
+  return v;
+}
+__device__ __forceinline__ void stg_stream_if(float* p, float v, unsigned ok) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q " LSFA_ST_STREAM " [%0], %1;\n}" ::"l"(p), "f"(v),
+               "r"(ok)
+               : "memory");
 }
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
   uint4 v;

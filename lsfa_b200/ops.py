@@ -311,7 +311,7 @@ def _build_args(key, flow, *, cur=None, scale_map=None, res=None, rnet_w=None, r
         scale_map=_ptr(scale_map), res=_ptr(res), rnet_w=_ptr(rnet_w), rnet_b=_ptr(rnet_b),
         cur=_ptr(cur), weight_mode=wm, logits=_ptr(logits), emb_warp=_ptr(emb_warp),
         emb_cur=_ptr(emb_cur), E=E, bypass=_ptr(bypass), out=_ptr(out), req=rq,
-        force_generic=int(bool(force_generic)))
+        force_generic=int(force_generic))
     lib = A.load()
     need = lib.lsfa_warp_scale_aggregate_workspace_bytes(args)
     if need:

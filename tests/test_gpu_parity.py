@@ -209,7 +209,8 @@ def run_fused(ops, cuda, d, mode_name, layout, use_scale=True, use_res=False, fl
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("mode_name,mode", MODES)
-@pytest.mark.parametrize("layout,generic", [("nchw", False), ("nchw", True), ("nhwc_f32", False)])
+# kernel choice for NCHW: 0 auto (all-TMA if it can), 1 generic gather, 2 plane-resident LDG/STG
+@pytest.mark.parametrize("layout,generic", [("nchw", 0), ("nchw", 1), ("nchw", 2), ("nhwc_f32", 0)])
 def test_fused_f32(ops, cuda, shape, mode_name, mode, layout, generic):
     N, C, H, W = shape
     d = make_case(hash((shape, mode)) % 1000, N, C, H, W, E=32 if mode == O.W_COSINE else 0,
@@ -233,7 +234,7 @@ def test_fused_bf16_nhwc(ops, cuda, shape, mode_name, mode):
     assert_close_bf16(got, want, what="%s %s" % (shape, mode_name))
 
 
-@pytest.mark.parametrize("layout,generic", [("nchw", False), ("nchw", True), ("nhwc_f32", False), ("nhwc_bf16", False)])
+@pytest.mark.parametrize("layout,generic", [("nchw", 0), ("nchw", 1), ("nchw", 2), ("nhwc_f32", 0), ("nhwc_bf16", 0)])
 def test_cur_frame_path_as_shipped(ops, cuda, layout, generic):
     """get_cur_test_symbol (SYM:570-586): warp(MV) + rnet_conv0(res) + small-net feature, no scale."""
     d = make_case(101, 3, 64, 38, 63, with_res=True, raw="ragged")
@@ -257,6 +258,29 @@ def test_flow_sources_agree(ops, cuda, flow_kind):
     assert np.array_equal(base.view(np.uint32), got.view(np.uint32))
 
 
+@pytest.mark.parametrize("variant", ["warp", "scale", "scale_cur", "res_cur"])
+@pytest.mark.parametrize("shape", [(5, 64, 38, 63), (3, 16, 60, 60), (2, 8, 16, 24), (1, 4, 38, 63)])
+def test_all_tma_kernel_every_variant(ops, cuda, variant, shape):
+    """force_generic=3 pins the warp-specialised all-TMA kernel; it must serve these shapes and agree
+    with the oracle (bypass frames included: their cur is carried HBM -> smem -> HBM by TMA alone)."""
+    N, C, H, W = shape
+    d = make_case(7 + N, N, C, H, W, with_res=(variant == "res_cur"), with_bypass=(variant in ("scale_cur", "res_cur") and N >= 3))
+    scale = max(np.abs(d["key"]).max(), np.abs(d["cur"]).max())
+    if variant == "warp":
+        want = oracle_fused(d, O.W_NONE, use_scale=False)
+        got = run_fused(ops, cuda, d, "none", "nchw", use_scale=False, force_generic=3)
+    elif variant == "scale":
+        want = oracle_fused(d, O.W_NONE)
+        got = run_fused(ops, cuda, d, "none", "nchw", force_generic=3)
+    elif variant == "scale_cur":
+        want = oracle_fused(d, O.W_LOGITS)
+        got = run_fused(ops, cuda, d, "logits", "nchw", force_generic=3)
+    else:
+        want = oracle_fused(d, O.W_ADD, use_scale=False, use_res=True)
+        got = run_fused(ops, cuda, d, "add", "nchw", use_scale=False, use_res=True, force_generic=3)
+    assert_close_f32(host(got), want, scale=scale, what="tma %s %s" % (variant, shape))
+
+
 def test_shared_key_feature_tile_as(ops, cuda):
     """get_batch_test_symbol (SYM:675-680): one key feature, many frames (tile_as -> key_index)."""
     d = make_case(9, 5, 32, 38, 63, shared_key=True)
@@ -269,7 +293,7 @@ def test_shared_key_feature_tile_as(ops, cuda):
 def test_req_add_and_null(ops, cuda):
     d = make_case(21, 2, 16, 38, 63)
     want = oracle_fused(d, O.W_LOGITS)
-    for layout, generic in (("nchw", False), ("nchw", True), ("nhwc_f32", False)):
+    for layout, generic in (("nchw", 0), ("nchw", 1), ("nchw", 2), ("nhwc_f32", 0)):
         first = run_fused(ops, cuda, d, "logits", layout, force_generic=generic)
         if layout == "nchw":
             acc = run_fused(ops, cuda, d, "logits", layout, force_generic=generic, req="add", out=first)
@@ -282,11 +306,13 @@ def test_req_add_and_null(ops, cuda):
 def test_plane_generic_nhwc_identical_bits(ops, cuda):
     """The three f32 kernels evaluate the same fmaf chain: results must agree bit for bit."""
     d = make_case(33, 3, 64, 38, 63, with_bypass=True)
-    a = host(run_fused(ops, cuda, d, "logits", "nchw"))
-    b = host(run_fused(ops, cuda, d, "logits", "nchw", force_generic=True))
+    a = host(run_fused(ops, cuda, d, "logits", "nchw", force_generic=3))      # all-TMA
+    b = host(run_fused(ops, cuda, d, "logits", "nchw", force_generic=1))      # generic gather
     c = host(run_fused(ops, cuda, d, "logits", "nhwc_f32"))
+    e = host(run_fused(ops, cuda, d, "logits", "nchw", force_generic=2))      # plane-resident LDG/STG
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+    assert np.array_equal(a.view(np.uint32), e.view(np.uint32))
 
 
 def test_unfused_chain_matches_fused(ops, cuda):
@@ -410,8 +436,12 @@ def test_full_batch_properties(ops, cuda):
     assert float((w12 - (w1 + w2)).abs().max()) <= 1e-5
     full = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits)
     gen = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits,
-                                   force_generic=True)
+                                   force_generic=1)
     assert torch.equal(full, gen)
+    pl = ops.warp_scale_aggregate(key1, mv, flow_kind="raw", cur=cur, weight_mode="logits", logits=logits,
+                                  force_generic=2)
+    assert torch.equal(full, pl)
+    del gen, pl
     # convexity: softmax weights sum to 1 -> out between min and max of the two sources
     lo = torch.minimum(w1, cur) - 1e-5
     hi = torch.maximum(w1, cur) + 1e-5

@@ -116,7 +116,10 @@ typedef struct LsfaAggArgs {
   void*   out;               /* (N,C,H,W) | (N,H,W,C) */
   int32_t req;               /* LSFA_REQ_* */
 
-  void*   workspace;         /* lsfa_warp_scale_aggregate_workspace_bytes() bytes, or NULL if 0 */
+  void*   workspace;         /* optional scratch of lsfa_warp_scale_aggregate_workspace_bytes() bytes:
+                                required for NCHW + COSINE (per-pixel logits); otherwise it only enables
+                                dynamic work claiming in the all-TMA kernel (NULL = static split).
+                                Contents need no initialisation; one workspace per in-flight call. */
   size_t  workspace_bytes;
 
   int32_t force_generic;     /* kernel choice (NCHW): 0 auto, 1 generic gather, 2 plane-resident LDG/STG,

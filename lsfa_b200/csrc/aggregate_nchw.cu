@@ -225,7 +225,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     const unsigned off_scale = (key_bytes + 127u) / 128u * 128u;
     const unsigned off_io = has_scale ? off_scale + (io_bytes + 127u) / 128u * 128u : off_scale;
     const unsigned stage_bytes = off_io + (io_bytes + 127u) / 128u * 128u;
-    long long stages = ((long long)kSmemMax - kBarrierBytes - (long long)res_bytes - (long long)pad) / stage_bytes;
+    long long stages = ((long long)kSmemMax - kTmaHeaderBytes - (long long)res_bytes - (long long)pad) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 3 && !(i == 1 && stages >= 2)) continue;    // want >= 3 stages; K=1 may run with 2
     P.K = K;
@@ -239,7 +239,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     P.off_scale = off_scale;
     P.off_io = off_io;
     P.items = (long long)P.N * P.chunks;
-    *smem_out = kBarrierBytes + (size_t)P.stages * stage_bytes + res_bytes + pad;
+    *smem_out = kTmaHeaderBytes + (size_t)P.stages * stage_bytes + res_bytes + pad;
     return true;
   }
   return false;
@@ -248,6 +248,10 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
 cudaError_t launch_agg_nchw_tma(const AggParams& P, size_t smem, cudaStream_t st) {
   long long grid = sm_count();
   if (grid > P.items) grid = P.items;
+  if (P.sched) {  // the per-frame claim counters start every launch at zero (enqueue-only, no sync)
+    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+  }
   switch (variant_of(P)) {
     case kVarWarpOnly: return launch_tma_variant<kVarWarpOnly>(P, smem, (int)grid, st);
     case kVarScale: return launch_tma_variant<kVarScale>(P, smem, (int)grid, st);

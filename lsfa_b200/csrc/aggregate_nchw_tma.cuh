@@ -13,7 +13,9 @@
 //
 // Pipeline (S stages, S >= 2):  full[s]  : producer -> consumers   (TMA bytes landed)
 //                               done[s]  : consumers -> producer   (stage computed, out in smem)
-//   producer: wait done[c] -> TMA-store stage c -> wait_group.read -> TMA-load item c+S into it
+//   producer: wait done[c] -> TMA-store stage c -> wait_group.read -> TMA-load the next item into it
+// Work is handed out dynamically (per-frame queues in a caller-supplied scratch) so that SMs
+// with more bandwidth do more items; each stage carries its (frame, chunk) descriptor in smem.
 #pragma once
 #include "aggregate_nchw_plane.cuh"
 
@@ -33,6 +35,9 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+constexpr int kTmaHeaderBytes = 256;   // 16 mbarriers + one item descriptor per stage
+constexpr int kTmaClaim = 4;           // items per dynamic claim (4 x ~1.8 us of work)
+
 template <int K, int PPT, int VAR>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
@@ -43,15 +48,13 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* done = full + kMaxStages;
-  unsigned char* ring = smem_raw + kBarrierBytes;
-  float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);  // [3][PPT*512]
+  volatile int2* desc = reinterpret_cast<volatile int2*>(smem_raw + 128);   // (frame, chunk) of each stage; frame < 0 = stop
+  unsigned char* ring = smem_raw + kTmaHeaderBytes;
+  float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);  // [3][PPT*480]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
-  const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
   const bool has_bypass = P.bypass != nullptr;
-  const size_t chunk_elems = (size_t)K * P.HW;
 
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -62,57 +65,107 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   }
   __syncthreads();
 
-  // item = (frame n, channel chunk); pixel parts are not used by this kernel (plan: parts == 1)
-  auto frame_of = [&](long long it, int& n, int& chunk) {
-    n = (int)(it / P.chunks);
-    chunk = (int)(it - (long long)n * P.chunks);
-  };
-
   if (warp == kTmaConsumerWarps) {
     // =========================== producer warp (one elected lane) ===========================
     if ((tid & 31) == 0) {
-      int ln, lchunk;          // load cursor
-      frame_of(i0, ln, lchunk);
-      long long lit = i0;
-      auto issue_loads = [&](int s) {
-        const bool byp = has_bypass && __ldg(P.bypass + ln) != 0;
+      // ---- work source: dynamic per-frame queues (sched != NULL) or a static contiguous range ----
+      // Dynamic: every frame f has a counter of claimed channel chunks.  A CTA stays on its frame
+      // (the consumers' sampling records are per frame) and claims kTmaClaim chunks at a time;
+      // when the frame is exhausted it hops to the next one.  SMs that see more bandwidth simply
+      // claim more, which removes the 20-25% tail a static split shows on B200 (unequal GPCs).
+      unsigned* sched = P.sched;
+      int f = (int)(((long long)blockIdx.x * P.N) / gridDim.x), c = 0, cend = 0, hops = 0;
+      if (sched == nullptr) {                         // static: items [i0, i1) of the (frame, chunk) grid
+        const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
+        const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
+        f = (int)(i0 / P.chunks);
+        c = (int)(i0 - (long long)f * P.chunks);
+        hops = (int)(i1 - i0);                        // static mode: items left
+        cend = P.chunks;
+      }
+      auto next_item = [&](int& n, int& chunk) -> bool {
+        if (sched == nullptr) {
+          if (hops <= 0) return false;
+          --hops;
+          n = f;
+          chunk = c;
+          if (++c == P.chunks) {
+            c = 0;
+            ++f;
+          }
+          return true;
+        }
+        while (true) {
+          if (c < cend) {
+            n = f;
+            chunk = c++;
+            return true;
+          }
+          if (hops >= P.N) return false;              // every frame has been seen exhausted
+          const int got = (int)atomicAdd(sched + f, (unsigned)kTmaClaim);
+          if (got < P.chunks) {
+            c = got;
+            cend = min(got + kTmaClaim, P.chunks);
+          } else {
+            f = (f + 1 == P.N) ? 0 : f + 1;
+            ++hops;
+          }
+        }
+      };
+      auto issue_loads = [&](int s, int n, int chunk) {
+        const bool byp = has_bypass && __ldg(P.bypass + n) != 0;
         unsigned char* st = ring + (size_t)s * P.stage_bytes;
-        const size_t e0 = ((size_t)ln * P.C + (size_t)lchunk * K) * P.HW;
+        const size_t e0 = ((size_t)n * P.C + (size_t)chunk * K) * P.HW;
         uint32_t bytes = has_cur ? P.io_bytes : 0u;
         if (!byp) bytes += P.key_bytes + (has_scale ? P.io_bytes : 0u);
-        mbar_expect_tx(&full[s], bytes);
+        desc[s].x = n;
+        desc[s].y = chunk;
+        mbar_expect_tx(&full[s], bytes);              // release: the descriptor is visible with the data
         if (!byp) {
-          const int kn = P.key_index ? __ldg(P.key_index + ln) : ln;
-          const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)lchunk * K) * P.HWk;
+          const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+          const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
           bulk_g2s(st, ksrc, P.key_bytes, &full[s]);
           if (has_scale) bulk_g2s(st + P.off_scale, static_cast<const float*>(P.scale) + e0, P.io_bytes, &full[s]);
         }
         if (has_cur) bulk_g2s(st + P.off_io, static_cast<const float*>(P.cur) + e0, P.io_bytes, &full[s]);
-        ++lit;
-        if (++lchunk == P.chunks) {
-          lchunk = 0;
-          ++ln;
-        }
       };
-      for (int s = 0; s < P.stages && lit < i1; ++s) issue_loads(s);
+      auto issue_stop = [&](int s) {
+        desc[s].x = -1;
+        desc[s].y = 0;
+        mbar_arrive(&full[s]);
+      };
 
-      int sn, schunk;          // store cursor
-      frame_of(i0, sn, schunk);
+      int n, chunk;
+      int live = 0;                                    // stages holding a real item
+      bool stopped = false;
+      for (int s = 0; s < P.stages; ++s) {
+        if (next_item(n, chunk)) {
+          issue_loads(s, n, chunk);
+          ++live;
+        } else {
+          issue_stop(s);
+          stopped = true;
+          break;
+        }
+      }
       int s = 0;
       unsigned ph = 0;
-      for (long long c = i0; c < i1; ++c) {
+      while (live > 0) {
         mbar_wait(&done[s], ph);                       // consumers finished this stage; out is in smem
         unsigned char* st = ring + (size_t)s * P.stage_bytes;
-        float* dst = static_cast<float*>(P.out) + ((size_t)sn * P.C + (size_t)schunk * K) * P.HW;
+        float* dst = static_cast<float*>(P.out) + ((size_t)desc[s].x * P.C + (size_t)desc[s].y * K) * P.HW;
         bulk_s2g(dst, st + P.off_io, P.io_bytes);
         bulk_commit();
-        if (lit < i1) {
-          bulk_wait_read_all();                        // the store has drained the stage: safe to refill
-          issue_loads(s);
-        }
-        if (++schunk == P.chunks) {
-          schunk = 0;
-          ++sn;
+        --live;
+        if (!stopped) {
+          if (next_item(n, chunk)) {
+            bulk_wait_read_all();                      // the store has drained the stage: safe to refill
+            issue_loads(s, n, chunk);
+            ++live;
+          } else {
+            issue_stop(s);
+            stopped = true;
+          }
         }
         if (++s == P.stages) {
           s = 0;
@@ -129,15 +182,17 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   unsigned o_top[PPT], o_bot[PPT];
   unsigned valid = 0;
   int cur_n = -1;
-  int n, chunk;
-  frame_of(i0, n, chunk);
   int s = 0;
   unsigned ph = 0;
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
   const unsigned io_plane_bytes = (unsigned)P.HW * 4u;
   (void)ww;
 
-  for (long long it = i0; it < i1; ++it) {
+  while (true) {
+    mbar_wait(&full[s], ph);
+    const int n = desc[s].x;
+    if (n < 0) break;
+    const int chunk = desc[s].y;
     const bool byp = has_bypass && (__ldg(P.bypass + n) != 0);
     if (n != cur_n) {  // new frame: rebuild this thread's sampling records
       cur_n = n;
@@ -171,7 +226,6 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       }
     }
 
-    mbar_wait(&full[s], ph);
     if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
       unsigned char* stage_s = ring + (size_t)s * P.stage_bytes;
       const int c0 = chunk * K;
@@ -220,10 +274,6 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
     if (++s == P.stages) {
       s = 0;
       ph ^= 1u;
-    }
-    if (++chunk == P.chunks) {
-      chunk = 0;
-      ++n;
     }
   }
 }

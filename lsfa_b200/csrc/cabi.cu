@@ -135,10 +135,15 @@ int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
   return LSFA_OK;
 }
 
+// Workspace layout (NCHW only): [cosine logits (N,2,H,W) f32, COSINE mode only][N claim counters]
 size_t cosine_ws_bytes(const LsfaAggArgs* a) {
   if (!a || a->weight_mode != LSFA_W_COSINE || a->layout != LSFA_LAYOUT_NCHW_F32) return 0;
   if (a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   return (size_t)a->N * 2 * a->H * a->W * sizeof(float);
+}
+size_t sched_ws_bytes(const LsfaAggArgs* a) {
+  if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0) return 0;
+  return ((size_t)a->N * sizeof(unsigned) + 15) / 16 * 16;
 }
 
 int run_aggregate(const LsfaAggArgs* a, void* stream) {
@@ -163,6 +168,10 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
       if (rc != LSFA_OK) return rc;
       P.logits = lg;
     }
+    // optional scratch for dynamic work claiming (all-TMA kernel); without it the split is static
+    const size_t ws_need = cosine_ws_bytes(a) + sched_ws_bytes(a);
+    if (a->workspace && a->workspace_bytes >= ws_need && (reinterpret_cast<uintptr_t>(a->workspace) % 4) == 0)
+      P.sched = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + cosine_ws_bytes(a));
     size_t smem = 0;
     // kernel choice: 0 auto (all-TMA, then plane-resident LDG/STG, then generic); the other
     // values pin one kernel for tests and ablations
@@ -276,7 +285,9 @@ int lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream) {
   return run_aggregate(args, stream);
 }
 
-size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) { return cosine_ws_bytes(args); }
+size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) {
+  return cosine_ws_bytes(args) + sched_ws_bytes(args);
+}
 
 int lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args) {
   if (!args || args->req == LSFA_REQ_NULL) return 0;

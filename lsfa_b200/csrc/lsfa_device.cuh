@@ -55,6 +55,7 @@ struct AggParams {
   long long items;
   // stage layout of the all-TMA kernel: [key planes | scale chunk | cur/out chunk]
   unsigned key_bytes, io_bytes, off_scale, off_io;
+  unsigned* sched;             // N zeroed counters for dynamic work claims, or NULL = static split
 };
 
 // ---------------------------------------------------------------------------------------

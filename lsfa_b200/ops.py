@@ -314,8 +314,10 @@ def _build_args(key, flow, *, cur=None, scale_map=None, res=None, rnet_w=None, r
         force_generic=int(force_generic))
     lib = A.load()
     need = lib.lsfa_warp_scale_aggregate_workspace_bytes(args)
+    if workspace is False and wm != A.W_COSINE:
+        need = 0                      # caller opts out of the scheduling scratch: static work split
     if need:
-        if workspace is None:
+        if workspace is None or workspace is False:
             workspace = torch.empty(need, dtype=torch.uint8, device=key.device)
         _dev(workspace, "workspace")
         if workspace.numel() * workspace.element_size() < need:

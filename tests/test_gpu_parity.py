@@ -281,6 +281,22 @@ def test_all_tma_kernel_every_variant(ops, cuda, variant, shape):
     assert_close_f32(host(got), want, scale=scale, what="tma %s %s" % (variant, shape))
 
 
+def test_all_tma_static_and_dynamic_split_agree(ops, cuda):
+    """With a workspace the all-TMA kernel claims work dynamically (per-frame queues); without one it
+    uses a static contiguous split.  Same bits either way, and repeated launches reuse the scratch."""
+    d = make_case(91, 9, 64, 38, 63, with_bypass=True)
+    t = lambda k: dev(d[k], cuda)  # noqa: E731
+    kw = dict(flow_kind="raw", cur=t("cur"), scale_map=t("scale_map"), weight_mode="logits", logits=t("logits"),
+              bypass=t("bypass"), force_generic=3)
+    dyn = ops.PreparedAggregate(t("key"), t("mv"), **kw)
+    a = host(dyn.run()).copy()
+    b = host(dyn.run()).copy()
+    st = host(ops.warp_scale_aggregate(t("key"), t("mv"), workspace=False, **kw))
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(a.view(np.uint32), st.view(np.uint32))
+    assert_close_f32(a, oracle_fused(d, O.W_LOGITS), scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="dyn")
+
+
 def test_shared_key_feature_tile_as(ops, cuda):
     """get_batch_test_symbol (SYM:675-680): one key feature, many frames (tile_as -> key_index)."""
     d = make_case(9, 5, 32, 38, 63, shared_key=True)

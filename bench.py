@@ -166,6 +166,7 @@ def cpu_reference_fps(sample_frames, reps, warmup, seed=0):
     import numpy as np
     from oracle import c_port
     c_port.build()
+    c_port.use_all_cores()
     host = make_host_inputs(sample_frames, seed, pinned=False)
     arr = {k: v.numpy() for k, v in host.items()}
     tmp = np.empty(5 * arr["key"].size, np.float32)

@@ -37,6 +37,14 @@ def num_threads():
     return load().lsfa_ref_num_threads()
 
 
+def use_all_cores():
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().lsfa_ref_set_num_threads(int(n))
+    return num_threads()
+
+
 def mv_pool(mv, im_scale=1.0, mode=0):
     mv = np.ascontiguousarray(mv, dtype=np.int32)
     N, h, w, _ = mv.shape

@@ -28,6 +28,15 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
+/* torchrun exports OMP_NUM_THREADS=1; the baseline is entitled to every host core it can use */
+EXPORT void lsfa_ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 EXPORT int lsfa_ref_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -1,6 +1,8 @@
 // NCHW float32 path: host-side planning / dispatch of the plane-resident kernel
 // (aggregate_nchw_plane.cuh, instantiated per variant in plane_var*.cu), the generic gather
 // kernel for shapes the fast kernel does not take, and the cosine-logit pre-pass.
+#include <cstdlib>
+
 #include "aggregate_nchw_tma.cuh"
 
 namespace lsfa {
@@ -35,12 +37,8 @@ agg_nchw_generic_kernel(const __grid_constant__ AggParams P) {
     return;
   }
   const int y = p / P.W, x = p - y * P.W;
-  float gx, gy;
-  pixel_grid(P, n, y, x, gx, gy);
-  PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
-  float bw, bc;
-  pixel_weights(P, n, p, bw, bc);
-  fold_blend(t, bw, bc);
+  const PixelLoads ld = issue_pixel_loads(P, n, y, x);
+  const PixelRec t = finish_pixel(P, ld, n, y, x);
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   if (P.res) {
     r0 = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
@@ -189,6 +187,40 @@ cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t 
   return launch_plane_variant<kVarRuntime>(P, smem, (int)grid, st);
 }
 
+// ---------------------------------------------------------------------------------------
+// Record pre-pass: every index-math row of the path (a3,a5,a6 MV pooling in float64, a7 grid,
+// a8 floor/weights, a13 softmax, blend fold) once per output pixel, written as a 32-byte packed
+// record.  The streaming kernel then rebuilds its per-frame state with two 16-byte loads per
+// pixel instead of redoing this math in every CTA that touches the frame (the sparse raw-MV
+// taps cost ~10 us of LSU time per rebuild: -8% on the fused kernel when done in place).
+// It runs just before the streaming kernel in stream order (~3 us for 64 frames).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agg_records_kernel(const __grid_constant__ AggParams P, uint4* __restrict__ rec) {
+  pdl_launch_dependents();
+  const long long total = (long long)P.N * P.HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / P.HW);
+    const int p = (int)(i - (long long)n * P.HW);
+    if (P.bypass != nullptr && __ldg(P.bypass + n) != 0) continue;   // never read for bypass frames
+    const int y = p / P.W, x = p - y * P.W;
+    const PixelLoads ld = issue_pixel_loads(P, n, y, x);
+    const PixelRec t = finish_pixel(P, ld, n, y, x);
+    uint4 a, b;
+    pack_record(t, a, b);
+    rec[2 * i] = a;
+    rec[2 * i + 1] = b;
+  }
+}
+
+cudaError_t launch_agg_records(const AggParams& P, uint4* rec, cudaStream_t st) {
+  const long long total = (long long)P.N * P.HW;
+  long long grid = (total + 255) / 256;
+  if (grid > 148LL * 8) grid = 148LL * 8;
+  agg_records_kernel<<<(unsigned)grid, 256, 0, st>>>(P, rec);
+  return cudaPeekAtLastError();
+}
+
 // ---- all-TMA kernel: planning and dispatch -------------------------------------------------
 static int variant_of(const AggParams& P) {
   const bool has_scale = P.scale != nullptr, has_cur = P.mode != LSFA_W_NONE, has_res = P.res != nullptr;
@@ -204,24 +236,33 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   const size_t kSmemMax = 227 * 1024;
   const int var = variant_of(P);
   if (var == kVarRuntime) return false;
-  if (P.HW > 8 * kTmaConsumers || P.HWk > 16383) return false;
+  if (P.HWk > 16383) return false;                               // tap byte offsets are packed in 16 bits
   const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
   for (const void* q : ptrs)
     if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
   if (((long long)P.C * P.HW) % 4 || ((long long)P.C * P.HWk) % 4) return false;
-  const int ppt_options[5] = {1, 2, 3, 5, 8};
-  int ppt = 8;
-  for (int i = 4; i >= 0; --i)
-    if ((long long)ppt_options[i] * kTmaConsumers >= P.HW) ppt = ppt_options[i];
+  // pixel slots per consumer thread; planes beyond 9*480 pixels are cut into balanced parts,
+  // which needs every plane slice 16-byte aligned (HW % 4 == 0)
+  const int ppt_options[6] = {1, 2, 3, 5, 7, 9};
+  const int max_part = 9 * kTmaConsumers;
+  const int parts = (P.HW + max_part - 1) / max_part;
+  if (parts > 1 && (P.HW % 4)) return false;
+  const int per_part = (P.HW + parts - 1) / parts;
+  int ppt = 9;
+  for (int i = 5; i >= 0; --i)
+    if ((long long)ppt_options[i] * kTmaConsumers >= per_part) ppt = ppt_options[i];
+  const int part_pix = ppt * kTmaConsumers;
+  if ((long long)part_pix * (parts - 1) >= P.HW) return false;   // every part must be non-empty
   const bool has_scale = var == kVarScale || var == kVarScaleCur;
-  const size_t res_bytes = var == kVarResCur ? (size_t)3 * ppt * kTmaConsumers * 4 : 0;
-  const size_t pad = (((size_t)ppt * kTmaConsumers - P.HW) * 4 + 127) / 128 * 128;
+  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 : 0;
+  const int io_plane = parts == 1 ? P.HW : part_pix;             // elements per plane slice in a stage
+  const size_t pad = (((size_t)part_pix - (parts == 1 ? P.HW : 0)) * 4 + 127) / 128 * 128;
   const int prefer[2] = {2, 1};
   for (int i = 0; i < 2; ++i) {
     const int K = prefer[i];
     if (P.C % K) continue;
     if (((long long)K * P.HW) % 4 || ((long long)K * P.HWk) % 4) continue;   // 16-byte bulk copies
-    const unsigned key_bytes = (unsigned)((size_t)K * P.HWk * 4), io_bytes = (unsigned)((size_t)K * P.HW * 4);
+    const unsigned key_bytes = (unsigned)((size_t)K * P.HWk * 4), io_bytes = (unsigned)((size_t)K * io_plane * 4);
     const unsigned off_scale = (key_bytes + 127u) / 128u * 128u;
     const unsigned off_io = has_scale ? off_scale + (io_bytes + 127u) / 128u * 128u : off_scale;
     const unsigned stage_bytes = off_io + (io_bytes + 127u) / 128u * 128u;
@@ -230,27 +271,38 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     if (stages < 3 && !(i == 1 && stages >= 2)) continue;    // want >= 3 stages; K=1 may run with 2
     P.K = K;
     P.chunks = P.C / K;
-    P.parts = 1;
-    P.part_pix = ppt * kTmaConsumers;
+    P.parts = parts;
+    P.part_pix = part_pix;
     P.stages = (int)stages;
     P.stage_bytes = stage_bytes;
     P.key_bytes = key_bytes;
     P.io_bytes = io_bytes;
     P.off_scale = off_scale;
     P.off_io = off_io;
-    P.items = (long long)P.N * P.chunks;
+    P.items = (long long)P.N * parts * P.chunks;
     *smem_out = kTmaHeaderBytes + (size_t)P.stages * stage_bytes + res_bytes + pad;
     return true;
   }
   return false;
 }
 
-cudaError_t launch_agg_nchw_tma(const AggParams& P, size_t smem, cudaStream_t st) {
+cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st) {
+  AggParams P = Pin;
   long long grid = sm_count();
   if (grid > P.items) grid = P.items;
   if (P.sched) {  // the per-frame claim counters start every launch at zero (enqueue-only, no sync)
-    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * sizeof(unsigned), st);
+    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * P.parts * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
+  }
+  if (P.records) {  // pre-pass writes the records, the streaming kernel follows in stream order
+    AggParams R = P;
+    R.records = nullptr;
+    cudaError_t e = launch_agg_records(R, const_cast<uint4*>(P.records), st);
+    if (e != cudaSuccess) return e;
+    // Programmatic dependent launch would let the TMA pipeline fill while the pre-pass runs (~1%),
+    // but with cross-stream event waits between calls (lsfa_b200.host.HostAggregator) we measured
+    // corrupted results on driver 580 / CUDA 12.9, so it is opt-in for experiments only.
+    P.pdl = getenv("LSFA_ENABLE_PDL") ? 1 : 0;
   }
   switch (variant_of(P)) {
     case kVarWarpOnly: return launch_tma_variant<kVarWarpOnly>(P, smem, (int)grid, st);

@@ -142,29 +142,51 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
       cur_part = part;
       const int pend = min(P.HW, pix0 + P.part_pix);
       valid = 0;
+      // the old records are dead from here on: clearing them first frees their registers for the
+      // load batch below (otherwise ptxas spills the batch and every spill store waits on its load)
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
         o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
-        const int p = pix0 + tid + j * kPlaneThreads;
-        if (p < pend) {
-          valid |= 1u << j;
-          if (!byp) {
-            const int y = p / P.W, x = p - y * P.W;
-            float gx, gy;
-            pixel_grid(P, n, y, x, gx, gy);
-            PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
-            float bw, bc;
-            pixel_weights(P, n, p, bw, bc);
-            fold_blend(t, bw, bc);
-            w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
-            wc[j] = t.wc; ww[j] = t.ww;
-            o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
-            o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
-            if (has_res) {
+      }
+      // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
+      if (!byp) {
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-                res_s[k * P.part_pix + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+        for (int j = 0; j < PPT; ++j) {
+          const int p = pix0 + tid + j * kPlaneThreads;
+          if (p < pend) prefetch_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+      }
+      // phase A: the loads proper, a few pixel slots at a time (they now hit in L2)
+      constexpr int RG = PPT >= 3 ? 3 : PPT;              // slots per load batch (register budget)
+#pragma unroll
+      for (int j0 = 0; j0 < PPT; j0 += RG) {
+        PixelLoads ld[RG];
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          const int p = pix0 + tid + j * kPlaneThreads;
+          if (j < PPT && p < pend && !byp) ld[g] = issue_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+        // phase B: the arithmetic (float64 pooling, exact fp32 grid round trip, softmax, fold)
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          if (j >= PPT) continue;
+          const int p = pix0 + tid + j * kPlaneThreads;
+          if (p < pend) {
+            valid |= 1u << j;
+            if (!byp) {
+              const PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
+              w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+              wc[j] = t.wc; ww[j] = t.ww;
+              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+              if (has_res) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  res_s[k * P.part_pix + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+              }
             }
           }
         }

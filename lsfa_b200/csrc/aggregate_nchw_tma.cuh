@@ -73,9 +73,12 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       // (the consumers' sampling records are per frame) and claims kTmaClaim chunks at a time;
       // when the frame is exhausted it hops to the next one.  SMs that see more bandwidth simply
       // claim more, which removes the 20-25% tail a static split shows on B200 (unequal GPCs).
+      // A "virtual frame" is (frame, pixel part): planes larger than PPT*480 pixels are cut into
+      // parts, each with its own sampling records, queue and slice of the scale/cur/out streams.
       unsigned* sched = P.sched;
-      int f = (int)(((long long)blockIdx.x * P.N) / gridDim.x), c = 0, cend = 0, hops = 0;
-      if (sched == nullptr) {                         // static: items [i0, i1) of the (frame, chunk) grid
+      const int NV = P.N * P.parts;
+      int f = (int)(((long long)blockIdx.x * NV) / gridDim.x), c = 0, cend = 0, hops = 0;
+      if (sched == nullptr) {                         // static: items [i0, i1) of the (virtual frame, chunk) grid
         const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
         const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
         f = (int)(i0 / P.chunks);
@@ -101,33 +104,64 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
             chunk = c++;
             return true;
           }
-          if (hops >= P.N) return false;              // every frame has been seen exhausted
+          if (hops >= NV) return false;               // every queue has been seen exhausted
           const int got = (int)atomicAdd(sched + f, (unsigned)kTmaClaim);
           if (got < P.chunks) {
             c = got;
             cend = min(got + kTmaClaim, P.chunks);
           } else {
-            f = (f + 1 == P.N) ? 0 : f + 1;
+            f = (f + 1 == NV) ? 0 : f + 1;
             ++hops;
           }
         }
       };
-      auto issue_loads = [&](int s, int n, int chunk) {
+      auto issue_loads = [&](int s, int vf, int chunk) {
+        const int n = vf / P.parts, part = vf - n * P.parts;
         const bool byp = has_bypass && __ldg(P.bypass + n) != 0;
         unsigned char* st = ring + (size_t)s * P.stage_bytes;
-        const size_t e0 = ((size_t)n * P.C + (size_t)chunk * K) * P.HW;
-        uint32_t bytes = has_cur ? P.io_bytes : 0u;
-        if (!byp) bytes += P.key_bytes + (has_scale ? P.io_bytes : 0u);
-        desc[s].x = n;
+        const int pix0 = part * P.part_pix;
+        const uint32_t len_bytes = (uint32_t)(min(P.part_pix, P.HW - pix0)) * 4u;   // one plane's slice
+        // parts == 1: the K planes of a stream are one contiguous run; otherwise one copy per plane
+        const uint32_t io_tx = P.parts == 1 ? P.io_bytes : (uint32_t)K * len_bytes;
+        const size_t e0 = ((size_t)n * P.C + (size_t)chunk * K) * P.HW + pix0;
+        uint32_t bytes = has_cur ? io_tx : 0u;
+        if (!byp) bytes += P.key_bytes + (has_scale ? io_tx : 0u);
+        desc[s].x = vf;
         desc[s].y = chunk;
         mbar_expect_tx(&full[s], bytes);              // release: the descriptor is visible with the data
         if (!byp) {
           const int kn = P.key_index ? __ldg(P.key_index + n) : n;
           const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
           bulk_g2s(st, ksrc, P.key_bytes, &full[s]);
-          if (has_scale) bulk_g2s(st + P.off_scale, static_cast<const float*>(P.scale) + e0, P.io_bytes, &full[s]);
         }
-        if (has_cur) bulk_g2s(st + P.off_io, static_cast<const float*>(P.cur) + e0, P.io_bytes, &full[s]);
+        if (P.parts == 1) {
+          if (!byp && has_scale) bulk_g2s(st + P.off_scale, static_cast<const float*>(P.scale) + e0, P.io_bytes, &full[s]);
+          if (has_cur) bulk_g2s(st + P.off_io, static_cast<const float*>(P.cur) + e0, P.io_bytes, &full[s]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const size_t ek = e0 + (size_t)k * P.HW;
+            const uint32_t dk = (uint32_t)k * (uint32_t)P.part_pix * 4u;
+            if (!byp && has_scale) bulk_g2s(st + P.off_scale + dk, static_cast<const float*>(P.scale) + ek, len_bytes, &full[s]);
+            if (has_cur) bulk_g2s(st + P.off_io + dk, static_cast<const float*>(P.cur) + ek, len_bytes, &full[s]);
+          }
+        }
+      };
+      auto issue_store = [&](int s) {
+        const int vf = desc[s].x, chunk = desc[s].y;
+        const int n = vf / P.parts, part = vf - n * P.parts;
+        const int pix0 = part * P.part_pix;
+        unsigned char* st = ring + (size_t)s * P.stage_bytes;
+        float* dst = static_cast<float*>(P.out) + ((size_t)n * P.C + (size_t)chunk * K) * P.HW + pix0;
+        if (P.parts == 1) {
+          bulk_s2g(dst, st + P.off_io, P.io_bytes);
+        } else {
+          const uint32_t len_bytes = (uint32_t)(min(P.part_pix, P.HW - pix0)) * 4u;
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            bulk_s2g(dst + (size_t)k * P.HW, st + P.off_io + (uint32_t)k * (uint32_t)P.part_pix * 4u, len_bytes);
+        }
+        bulk_commit();
       };
       auto issue_stop = [&](int s) {
         desc[s].x = -1;
@@ -152,10 +186,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       unsigned ph = 0;
       while (live > 0) {
         mbar_wait(&done[s], ph);                       // consumers finished this stage; out is in smem
-        unsigned char* st = ring + (size_t)s * P.stage_bytes;
-        float* dst = static_cast<float*>(P.out) + ((size_t)desc[s].x * P.C + (size_t)desc[s].y * K) * P.HW;
-        bulk_s2g(dst, st + P.off_io, P.io_bytes);
-        bulk_commit();
+        issue_store(s);
         --live;
         if (!stopped) {
           if (next_item(n, chunk)) {
@@ -181,49 +212,113 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
   unsigned o_top[PPT], o_bot[PPT];
   unsigned valid = 0;
-  int cur_n = -1;
+  int cur_vf = -1, n = 0;
+  bool byp = false, pdl_synced = false;
   int s = 0;
   unsigned ph = 0;
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
-  const unsigned io_plane_bytes = (unsigned)P.HW * 4u;
+  const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
   (void)ww;
+  constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
 
   while (true) {
     mbar_wait(&full[s], ph);
-    const int n = desc[s].x;
-    if (n < 0) break;
+    const int vf = desc[s].x;
+    if (vf < 0) break;
     const int chunk = desc[s].y;
-    const bool byp = has_bypass && (__ldg(P.bypass + n) != 0);
-    if (n != cur_n) {  // new frame: rebuild this thread's sampling records
-      cur_n = n;
+    if (vf != cur_vf) {  // new frame (or pixel part): rebuild this thread's sampling records
+      cur_vf = vf;
+      n = vf / P.parts;
+      const int pix0 = (vf - n * P.parts) * P.part_pix;
+      const int pend = min(P.HW, pix0 + P.part_pix);
+      byp = has_bypass && (__ldg(P.bypass + n) != 0);
       valid = 0;
+      if (P.records != nullptr) {
+        // records come from the pre-pass (agg_records_kernel): two 16-byte loads per pixel slot
+        if (P.pdl && !pdl_synced) {
+          pdl_wait();                 // first use of the pre-pass's output
+          pdl_synced = true;
+        }
+        uint4 ra[PPT], rb[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const int p = pix0 + tid + j * kTmaConsumers;
+          ra[j] = rb[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (p < pend) {
+            valid |= 1u << j;
+            if (!byp) {
+              const uint4* rp = P.records + 2 * ((size_t)n * P.HW + p);
+              ra[j] = __ldg(rp);
+              rb[j] = __ldg(rp + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          w00[j] = __uint_as_float(ra[j].x); w01[j] = __uint_as_float(ra[j].y);
+          w10[j] = __uint_as_float(ra[j].z); w11[j] = __uint_as_float(ra[j].w);
+          wc[j] = __uint_as_float(rb[j].x); ww[j] = __uint_as_float(rb[j].y);
+          o_top[j] = rb[j].z; o_bot[j] = rb[j].w;
+          if (has_res) {
+            const int p = pix0 + tid + j * kTmaConsumers;
+            if (p < pend && !byp) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+            }
+          }
+        }
+      } else {
+      // the old records are dead from here on: clearing them first frees their registers for the
+      // load batch below (otherwise ptxas spills the batch and every spill store waits on its load)
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
-        o_top[j] = o_bot[j] = 0u;
-        const int p = tid + j * kTmaConsumers;
-        if (p < P.HW) {
-          valid |= 1u << j;
-          if (!byp) {
-            const int y = p / P.W, x = p - y * P.W;
-            float gx, gy;
-            pixel_grid(P, n, y, x, gx, gy);
-            PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
-            float bw, bc;
-            pixel_weights(P, n, p, bw, bc);
-            fold_blend(t, bw, bc);
-            w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
-            wc[j] = t.wc; ww[j] = t.ww;
-            o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
-            o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
-            if (has_res) {
+        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
+      }
+      // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
+      if (!byp) {
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-                res_s[k * (PPT * kTmaConsumers) + p] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+        for (int j = 0; j < PPT; ++j) {
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (p < pend) prefetch_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+      }
+      // phase A: the loads proper, a few pixel slots at a time (they now hit in L2)
+      constexpr int RG = PPT >= 3 ? 3 : PPT;              // slots per load batch (register budget)
+#pragma unroll
+      for (int j0 = 0; j0 < PPT; j0 += RG) {
+        PixelLoads ld[RG];
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (j < PPT && p < pend && !byp) ld[g] = issue_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+        // phase B: the arithmetic (float64 pooling, exact fp32 grid round trip, softmax, fold)
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          if (j >= PPT) continue;
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (p < pend) {
+            valid |= 1u << j;
+            if (!byp) {
+              const PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
+              w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+              wc[j] = t.wc; ww[j] = t.ww;
+              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+              if (has_res) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+              }
             }
           }
         }
       }
+      }  // in-kernel record build
     }
 
     if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
@@ -241,30 +336,39 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
         const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
         const float* sc_s = reinterpret_cast<const float*>(stage_s + P.off_scale + (size_t)k * io_plane_bytes) + tid;
         float* io_s = reinterpret_cast<float*>(stage_s + P.off_io + (size_t)k * io_plane_bytes) + tid;
-        float v00[PPT], v01[PPT], v10[PPT], v11[PPT], sc[PPT], cu[PPT];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {   // all shared-memory reads of the plane first ...
-          v00[j] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
-          v01[j] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
-          v10[j] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
-          v11[j] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
-          sc[j] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;   // slots past the plane read the tail pad
-          cu[j] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
-        }
+        for (int j0 = 0; j0 < PPT; j0 += JG) {
+          float v00[JG], v01[JG], v10[JG], v11[JG], sc[JG], cu[JG];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {   // ... then the arithmetic and the in-place stores
-          float v = w00[j] * v00[j];
-          v = fmaf(w01[j], v01[j], v);
-          v = fmaf(w10[j], v10[j], v);
-          v = fmaf(w11[j], v11[j], v);
-          if (has_scale) v *= sc[j];
-          if (has_res) {
-            const int q = tid + j * kTmaConsumers;
-            v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
-                                      res_s[2 * PPT * kTmaConsumers + q]), v);
+          for (int g = 0; g < JG; ++g) {   // all shared-memory reads of the group first ...
+            const int j = j0 + g;
+            if (j < PPT) {
+              v00[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+              v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+              v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+              v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+              sc[g] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;   // slots past the plane read the tail pad
+              cu[g] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
+            }
           }
-          const float o = has_cur ? fmaf(wc[j], cu[j], v) : v;
-          if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
+#pragma unroll
+          for (int g = 0; g < JG; ++g) {   // ... then the arithmetic and the in-place stores
+            const int j = j0 + g;
+            if (j < PPT) {
+              float v = w00[j] * v00[g];
+              v = fmaf(w01[j], v01[g], v);
+              v = fmaf(w10[j], v10[g], v);
+              v = fmaf(w11[j], v11[g], v);
+              if (has_scale) v *= sc[g];
+              if (has_res) {
+                const int q = tid + j * kTmaConsumers;
+                v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
+                                          res_s[2 * PPT * kTmaConsumers + q]), v);
+              }
+              const float o = has_cur ? fmaf(wc[j], cu[g], v) : v;
+              if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
+            }
+          }
         }
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
@@ -281,15 +385,25 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
 template <int VAR>
 cudaError_t launch_tma_variant(const AggParams& P, size_t smem, int grid, cudaStream_t st);
 
-#define LSFA_TMA_FOREACH_KP(X) X(1, 1) X(1, 2) X(1, 3) X(1, 5) X(1, 8) X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 8)
+#define LSFA_TMA_FOREACH_KP(X) \
+  X(1, 1) X(1, 2) X(1, 3) X(1, 5) X(1, 7) X(1, 9) X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 7) X(2, 9)
 
 #define LSFA_TMA_LAUNCH(VAR, KK, PP)                                                              \
   if (P.K == KK && ppt == PP) {                                                                   \
     auto kfn = agg_nchw_tma_kernel<KK, PP, VAR>;                                                  \
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                               \
-    kfn<<<grid, kTmaThreads, smem, st>>>(P);                                                      \
-    return cudaPeekAtLastError();                                                                 \
+    cudaLaunchConfig_t cfg = {};                                                                  \
+    cfg.gridDim = dim3((unsigned)grid);                                                           \
+    cfg.blockDim = dim3(kTmaThreads);                                                             \
+    cfg.dynamicSmemBytes = smem;                                                                  \
+    cfg.stream = st;                                                                              \
+    cudaLaunchAttribute attr[1];                                                                  \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+    cfg.attrs = attr;                                                                             \
+    cfg.numAttrs = P.pdl ? 1 : 0;                                                                 \
+    return cudaLaunchKernelEx(&cfg, kfn, P);                                                      \
   }
 
 }  // namespace lsfa

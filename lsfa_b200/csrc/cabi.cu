@@ -135,15 +135,20 @@ int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
   return LSFA_OK;
 }
 
-// Workspace layout (NCHW only): [cosine logits (N,2,H,W) f32, COSINE mode only][N claim counters]
+// Workspace layout (NCHW only): [cosine logits (N,2,H,W) f32, COSINE mode only][claim counters][records]
 size_t cosine_ws_bytes(const LsfaAggArgs* a) {
   if (!a || a->weight_mode != LSFA_W_COSINE || a->layout != LSFA_LAYOUT_NCHW_F32) return 0;
   if (a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   return (size_t)a->N * 2 * a->H * a->W * sizeof(float);
 }
+size_t records_ws_bytes(const LsfaAggArgs* a) {   // packed sampling records of the pre-pass: 32 B per output pixel
+  if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
+  return (size_t)a->N * a->H * a->W * 32;
+}
 size_t sched_ws_bytes(const LsfaAggArgs* a) {
-  if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0) return 0;
-  return ((size_t)a->N * sizeof(unsigned) + 15) / 16 * 16;
+  if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
+  const size_t parts = ((size_t)a->H * a->W + 4319) / 4320;      // pixel parts of the all-TMA kernel (9 x 480)
+  return ((size_t)a->N * parts * sizeof(unsigned) + 15) / 16 * 16;
 }
 
 int run_aggregate(const LsfaAggArgs* a, void* stream) {
@@ -169,9 +174,13 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
       P.logits = lg;
     }
     // optional scratch for dynamic work claiming (all-TMA kernel); without it the split is static
-    const size_t ws_need = cosine_ws_bytes(a) + sched_ws_bytes(a);
-    if (a->workspace && a->workspace_bytes >= ws_need && (reinterpret_cast<uintptr_t>(a->workspace) % 4) == 0)
-      P.sched = reinterpret_cast<unsigned*>(static_cast<char*>(a->workspace) + cosine_ws_bytes(a));
+    const size_t cos_b = (cosine_ws_bytes(a) + 15) / 16 * 16;
+    const size_t ws_need = cos_b + sched_ws_bytes(a) + records_ws_bytes(a);
+    if (a->workspace && a->workspace_bytes >= ws_need && (reinterpret_cast<uintptr_t>(a->workspace) % 16) == 0) {
+      char* ws = static_cast<char*>(a->workspace);
+      P.sched = reinterpret_cast<unsigned*>(ws + cos_b);
+      P.records = reinterpret_cast<const uint4*>(ws + cos_b + sched_ws_bytes(a));
+    }
     size_t smem = 0;
     // kernel choice: 0 auto (all-TMA, then plane-resident LDG/STG, then generic); the other
     // values pin one kernel for tests and ablations
@@ -286,12 +295,18 @@ int lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream) {
 }
 
 size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) {
-  return cosine_ws_bytes(args) + sched_ws_bytes(args);
+  return (cosine_ws_bytes(args) + 15) / 16 * 16 + sched_ws_bytes(args) + records_ws_bytes(args);
 }
 
 int lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args) {
   if (!args || args->req == LSFA_REQ_NULL) return 0;
-  return (args->weight_mode == LSFA_W_COSINE && args->layout == LSFA_LAYOUT_NCHW_F32) ? 2 : 1;
+  if (args->layout != LSFA_LAYOUT_NCHW_F32) return 1;
+  int n = 1;
+  if (args->weight_mode == LSFA_W_COSINE) ++n;                       // cosine-logit pre-pass
+  const size_t need = lsfa_warp_scale_aggregate_workspace_bytes(args);
+  if (args->workspace && args->workspace_bytes >= need && args->force_generic != 1 && args->force_generic != 2)
+    ++n;                                                             // record pre-pass (all-TMA kernel)
+  return n;
 }
 
 int lsfa_cosine_logits(const void* emb_warp, const void* emb_cur, float* logits, int N, int E, int H, int W,

@@ -56,6 +56,8 @@ struct AggParams {
   // stage layout of the all-TMA kernel: [key planes | scale chunk | cur/out chunk]
   unsigned key_bytes, io_bytes, off_scale, off_io;
   unsigned* sched;             // N zeroed counters for dynamic work claims, or NULL = static split
+  const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
+  int pdl;                     // launched as a programmatic dependent of the record pre-pass
 };
 
 // ---------------------------------------------------------------------------------------
@@ -234,6 +236,147 @@ __device__ __forceinline__ void pixel_weights(const AggParams& P, int n, int p, 
     softmax2(__ldg(l + p), __ldg(l + P.HW + p), ww, wc);
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// Split form of the record build: issue every global load of a pixel first (PixelLoads), do the
+// arithmetic later (finish_pixel).  A thread that owns several pixels issues the loads of all of
+// them back to back, so a record rebuild costs ONE trip to DRAM instead of two per pixel - under
+// a saturated HBM that trip is 2-3 us and was the largest non-streaming cost of the fused kernel.
+// ---------------------------------------------------------------------------------------
+struct PixelLoads {
+  unsigned t[8];   // raw MV: centre taps [row7: x7(ch0,ch1) x8(ch0,ch1)] [row8: ...]; flow/grid: t[0]=x, t[1]=y
+  float l0, l1;    // logits (warp, cur)
+};
+
+__device__ __forceinline__ uint2 ldg_u2_or_zero(const void* base, size_t elem, bool ok) {
+  uint2 v = make_uint2(0u, 0u);
+  if (ok) v = __ldg(reinterpret_cast<const uint2*>(base) + elem);
+  return v;
+}
+
+__device__ __forceinline__ PixelLoads issue_pixel_loads(const AggParams& P, int n, int y, int x) {
+  PixelLoads L;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) L.t[i] = 0u;
+  L.l0 = L.l1 = 0.0f;
+  const int p = y * P.W + x;
+  if (P.flow_kind == LSFA_FLOW_GRID || P.flow_kind == LSFA_FLOW_PREPOOLED) {
+    const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
+    L.t[0] = __float_as_uint(__ldg(f + p));
+    L.t[1] = __float_as_uint(__ldg(f + P.HW + p));
+  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+    // (x,y) pairs are 8 bytes: one 8-byte load per tap, zero beyond the unpadded image
+    const char* img = (const char*)P.flow + (size_t)n * P.mv_h * P.mv_w * 8;
+    const int y7 = 16 * y + 7, x7 = 16 * x + 7;
+    const uint2 a = ldg_u2_or_zero(img, (size_t)y7 * P.mv_w + x7, y7 < P.mv_h && x7 < P.mv_w);
+    const uint2 b = ldg_u2_or_zero(img, (size_t)y7 * P.mv_w + x7 + 1, y7 < P.mv_h && x7 + 1 < P.mv_w);
+    const uint2 c = ldg_u2_or_zero(img, (size_t)(y7 + 1) * P.mv_w + x7, y7 + 1 < P.mv_h && x7 < P.mv_w);
+    const uint2 d = ldg_u2_or_zero(img, (size_t)(y7 + 1) * P.mv_w + x7 + 1, y7 + 1 < P.mv_h && x7 + 1 < P.mv_w);
+    L.t[0] = a.x; L.t[1] = a.y; L.t[2] = b.x; L.t[3] = b.y;
+    L.t[4] = c.x; L.t[5] = c.y; L.t[6] = d.x; L.t[7] = d.y;
+  }
+  if (P.mode == LSFA_W_LOGITS || (P.mode == LSFA_W_COSINE && P.logits != nullptr)) {
+    const float* l = P.logits + (size_t)n * 2 * P.HW;
+    L.l0 = __ldg(l + p);
+    L.l1 = __ldg(l + P.HW + p);
+  }
+  return L;
+}
+
+// Register-free first touch of everything issue_pixel_loads() will read: L2 prefetches for all of
+// a thread's pixels go out back to back, so the loads that follow (one pixel at a time, because
+// ptxas will not keep 10 words x PPT pixels live next to the hot loop's state) hit in L2.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void prefetch_pixel_loads(const AggParams& P, int n, int y, int x) {
+  const int p = y * P.W + x;
+  if (P.flow_kind == LSFA_FLOW_GRID || P.flow_kind == LSFA_FLOW_PREPOOLED) {
+    const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
+    prefetch_l2(f + p);
+    prefetch_l2(f + P.HW + p);
+  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+    const char* img = (const char*)P.flow + (size_t)n * P.mv_h * P.mv_w * 8;
+    const int y7 = 16 * y + 7, x7 = 16 * x + 7;   // x7 and x7+1 share a 32-byte sector unless x7*8 % 32 == 24
+    if (y7 < P.mv_h && x7 < P.mv_w) prefetch_l2(img + ((size_t)y7 * P.mv_w + x7) * 8);
+    if (y7 < P.mv_h && x7 + 1 < P.mv_w) prefetch_l2(img + ((size_t)y7 * P.mv_w + x7 + 1) * 8);
+    if (y7 + 1 < P.mv_h && x7 < P.mv_w) prefetch_l2(img + ((size_t)(y7 + 1) * P.mv_w + x7) * 8);
+    if (y7 + 1 < P.mv_h && x7 + 1 < P.mv_w) prefetch_l2(img + ((size_t)(y7 + 1) * P.mv_w + x7 + 1) * 8);
+  }
+  if (P.mode == LSFA_W_LOGITS || (P.mode == LSFA_W_COSINE && P.logits != nullptr)) {
+    const float* l = P.logits + (size_t)n * 2 * P.HW;
+    prefetch_l2(l + p);
+    prefetch_l2(l + P.HW + p);
+  }
+}
+
+__device__ __forceinline__ double raw_word(unsigned w, bool is_i32) {
+  return is_i32 ? (double)(int)w : (double)__uint_as_float(w);
+}
+
+// Everything after the loads: a5/a6 pooling in float64, a7 grid, a8 index math, blend weights.
+__device__ __forceinline__ PixelRec finish_pixel(const AggParams& P, const PixelLoads& L, int n, int y,
+                                                 int x, bool fold = true) {
+  float gx, gy;
+  if (P.flow_kind == LSFA_FLOW_GRID) {
+    gx = __uint_as_float(L.t[0]);
+    gy = __uint_as_float(L.t[1]);
+  } else {
+    float fx, fy;
+    if (P.flow_kind == LSFA_FLOW_PREPOOLED) {
+      fx = __uint_as_float(L.t[0]);
+      fy = __uint_as_float(L.t[1]);
+    } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+      const bool i32 = P.flow_kind == LSFA_FLOW_RAW_I32;
+      // ((a + b) + (c + d)) * 0.25 * (im_scale / 16), cv2's horizontal-pass-first order
+      const double sx = __dmul_rn(__dadd_rn(__dadd_rn(raw_word(L.t[0], i32), raw_word(L.t[2], i32)),
+                                            __dadd_rn(raw_word(L.t[4], i32), raw_word(L.t[6], i32))), 0.25);
+      const double sy = __dmul_rn(__dadd_rn(__dadd_rn(raw_word(L.t[1], i32), raw_word(L.t[3], i32)),
+                                            __dadd_rn(raw_word(L.t[5], i32), raw_word(L.t[7], i32))), 0.25);
+      fx = (float)__dmul_rn(sx, P.mv_scale);
+      fy = (float)__dmul_rn(sy, P.mv_scale);
+    } else {  // avg16: 256 taps, not prefetched (not the parity mode)
+      if (P.flow_kind == LSFA_FLOW_RAW_I32) {
+        const int* mv = (const int*)P.flow + (size_t)n * P.mv_h * P.mv_w * 2;
+        fx = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 0, P.pool_mode), P.mv_scale);
+        fy = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 1, P.pool_mode), P.mv_scale);
+      } else {
+        const float* mv = (const float*)P.flow + (size_t)n * P.mv_h * P.mv_w * 2;
+        fx = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 0, P.pool_mode), P.mv_scale);
+        fy = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 1, P.pool_mode), P.mv_scale);
+      }
+    }
+    gx = exact_grid(fx, (float)x, P.half_w);
+    gy = exact_grid(fy, (float)y, P.half_h);
+  }
+  PixelRec t = make_taps(gx, gy, P.Hk, P.Wk, P.wk_m1, P.hk_m1);
+  if (fold) {
+    float ww = 1.0f, wc = 0.0f;
+    if (P.mode == LSFA_W_ADD) {
+      wc = 1.0f;
+    } else if (P.mode == LSFA_W_MEAN) {
+      ww = 0.5f;
+      wc = 0.5f;
+    } else if (P.mode == LSFA_W_LOGITS || P.mode == LSFA_W_COSINE) {
+      softmax2(L.l0, L.l1, ww, wc);
+    }
+    fold_blend(t, ww, wc);
+  }
+  return t;
+}
+
+// Packed sampling record exchanged between the record pre-pass and the streaming kernel:
+// two 16-byte words per output pixel.
+__device__ __forceinline__ void pack_record(const PixelRec& t, uint4& a, uint4& b) {
+  a = make_uint4(__float_as_uint(t.w00), __float_as_uint(t.w01), __float_as_uint(t.w10), __float_as_uint(t.w11));
+  b = make_uint4(__float_as_uint(t.wc), __float_as_uint(t.ww),
+                 (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16),
+                 (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16));
+}
+
+// programmatic dependent launch (PDL): the pre-pass lets its dependent start early; the dependent
+// waits for the pre-pass's memory only where it first needs it
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (global -> shared), SASS: SYNCS / UBLKCP

@@ -166,7 +166,7 @@ def test_bilinear_sampler_matches_torch_grid_sample(ops, cuda):
 # the fused operator: every weight mode x layout x kernel
 # ------------------------------------------------------------------------------------------
 MODES = [("none", O.W_NONE), ("add", O.W_ADD), ("mean", O.W_MEAN), ("logits", O.W_LOGITS), ("cosine", O.W_COSINE)]
-SHAPES = [(3, 64, 38, 63), (2, 8, 68, 120), (4, 16, 7, 9), (2, 32, 37, 63)]
+SHAPES = [(3, 64, 38, 63), (2, 8, 68, 120), (4, 16, 7, 9), (2, 32, 37, 63), (1, 8, 69, 67)]
 
 
 def run_fused(ops, cuda, d, mode_name, layout, use_scale=True, use_res=False, flow_kind="raw",
@@ -259,7 +259,7 @@ def test_flow_sources_agree(ops, cuda, flow_kind):
 
 
 @pytest.mark.parametrize("variant", ["warp", "scale", "scale_cur", "res_cur"])
-@pytest.mark.parametrize("shape", [(5, 64, 38, 63), (3, 16, 60, 60), (2, 8, 16, 24), (1, 4, 38, 63)])
+@pytest.mark.parametrize("shape", [(5, 64, 38, 63), (3, 16, 60, 60), (2, 8, 16, 24), (1, 4, 38, 63), (3, 8, 68, 120), (2, 4, 100, 132)])
 def test_all_tma_kernel_every_variant(ops, cuda, variant, shape):
     """force_generic=3 pins the warp-specialised all-TMA kernel; it must serve these shapes and agree
     with the oracle (bypass frames included: their cur is carried HBM -> smem -> HBM by TMA alone)."""

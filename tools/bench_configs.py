@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Kernel-level numbers for every BASELINE.json config and variant (device-resident inputs,
+generated on the device; CUDA events; one JSON line per row).  Not the driver's bench - see
+bench.py for the contract line.  Usage: python tools/bench_configs.py [--quick]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lsfa_b200 import ops  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def time_ms(fn, warmup=5, steps=30):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def synth(N, C, H, W, mvh, mvw, dev, max_px=32, E=0):
+    g = torch.Generator(device=dev).manual_seed(0)
+    d = {
+        "key": torch.randn((N, C, H, W), device=dev, generator=g).clamp_(min=0),
+        "cur": torch.randn((N, C, H, W), device=dev, generator=g).clamp_(min=0),
+        "scale_map": 1 + 0.1 * torch.randn((N, C, H, W), device=dev, generator=g),
+        "logits": torch.randn((N, 2, H, W), device=dev, generator=g),
+    }
+    bh, bw = -(-mvh // 16), -(-mvw // 16)
+    blk = torch.randint(-max_px, max_px + 1, (N, bh, bw, 2), device=dev, generator=g, dtype=torch.int32)
+    blk[torch.rand((N, bh, bw), device=dev, generator=g) < 0.5] = 0
+    d["mv"] = blk.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :mvh, :mvw].contiguous()
+    d["res"] = torch.randn((N, 3, H, W), device=dev, generator=g) * 30
+    d["rnet_w"] = 0.01 * torch.randn((C, 3), device=dev, generator=g)
+    d["rnet_b"] = torch.zeros((C,), device=dev)
+    if E:
+        d["emb_warp"] = torch.randn((N, E, H, W), device=dev, generator=g)
+        d["emb_cur"] = torch.randn((N, E, H, W), device=dev, generator=g)
+    return d
+
+
+def row(name, frames, alg_bytes_per_frame, ms, pk, note=""):
+    gbs = frames * alg_bytes_per_frame / (ms / 1e3) / 1e9
+    r = {"config": name, "frames": frames, "ms_per_step": round(ms, 4), "frames_per_s": round(frames / (ms / 1e3), 1),
+         "alg_bytes_per_frame": alg_bytes_per_frame, "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / pk, 4),
+         "frac_of_8TBs": round(gbs / 8000.0, 4), "note": note}
+    print(json.dumps(r), flush=True)
+    return r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    pk = peak()
+    s = torch.cuda.current_stream().cuda_stream
+    C, H, W = 1024, 38, 63
+    HW = H * W
+    F4, F2 = C * HW * 4, C * HW * 2
+
+    # ---- configs 1/2: fp32 NCHW, 38x63 ----
+    N = 64
+    d = synth(N, C, H, W, 600, 1000, dev, E=0)
+    flow = ops.mv_pool(d["mv"])
+    grid = ops.GridGenerator(flow)
+    out = torch.empty_like(d["key"])
+    row("cfg1 V0 GridGenerator+BilinearSampler (2 ops, fp32 NCHW)", N, 2 * F4 + 8 * HW,
+        time_ms(lambda: ops.BilinearSampler(d["key"], ops.GridGenerator(flow, out=grid), out=out)), pk, "drop-in operators")
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw")
+    row("cfg1 V0 fused warp only, raw MV pooled in-kernel", N, 2 * F4 + 32 * HW, time_ms(lambda: p.run(s)), pk)
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], res=d["res"], rnet_w=d["rnet_w"],
+                              rnet_b=d["rnet_b"], weight_mode="add")
+    row("V1 shipped non-key path: warp + rnet(res) + cur", N, 3 * F4 + 32 * HW + 12 * HW + 16384, time_ms(lambda: p.run(s)), pk)
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                              weight_mode="logits", logits=d["logits"])
+    row("cfg2 V2 fused warp*scale + logits blend (headline, all-TMA)", N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk)
+    for fk, fl in (("flow", flow), ("grid", grid)):
+        p = ops.PreparedAggregate(d["key"], fl, flow_kind=fk, cur=d["cur"], scale_map=d["scale_map"],
+                                  weight_mode="logits", logits=d["logits"])
+        row("cfg2 V2 all-TMA, %s given (no in-kernel MV pooling)" % fk, N, 4 * F4 + 16 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                              weight_mode="logits", logits=d["logits"], workspace=False)
+    row("cfg2 V2 all-TMA, static work split (no scratch)", N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    for fg, nm in ((2, "plane-resident LDG/STG kernel"), (1, "generic gather kernel")):
+        p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                                  weight_mode="logits", logits=d["logits"], force_generic=fg)
+        row("cfg2 V2 " + nm, N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    tmp = torch.empty(5 * d["key"].numel(), dtype=torch.float32, device=dev)
+    row("cfg2 V2 UNFUSED op-by-op chain (9 kernels)", N, 4 * F4 + 40 * HW,
+        time_ms(lambda: ops.unfused_chain(d["key"], flow, d["scale_map"], d["cur"], d["logits"], tmp), 3, 10), pk,
+        "algorithmic bytes of the fused op; real traffic is 16F")
+    del tmp
+    if not args.quick:
+        E = 2048
+        g = torch.Generator(device=dev).manual_seed(1)
+        Nc = 16
+        ew = torch.randn((Nc, E, H, W), device=dev, generator=g)
+        ec = torch.randn((Nc, E, H, W), device=dev, generator=g)
+        p = ops.PreparedAggregate(d["key"][:Nc], d["mv"][:Nc], flow_kind="raw", cur=d["cur"][:Nc], scale_map=d["scale_map"][:Nc],
+                                  weight_mode="cosine", emb_warp=ew, emb_cur=ec)
+        row("V3 cosine (Fgfa) fp32 NCHW: cosine pre-pass + fused", Nc, 4 * F4 + 40 * HW + 2 * E * HW * 4, time_ms(lambda: p.run(s)), pk,
+            "2 launches")
+        del ew, ec
+
+    # ---- config 3: bf16 NHWC ----
+    Nb = 128 if args.quick else 512
+    reps = Nb // N
+    nh = {k: ops.to_nhwc(d[k], torch.bfloat16).repeat(reps, 1, 1, 1) for k in ("key", "cur", "scale_map")}
+    mvb = d["mv"].repeat(reps, 1, 1, 1)
+    lgb = d["logits"].repeat(reps, 1, 1, 1)
+    p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
+                              weight_mode="logits", logits=lgb, layout="nhwc_bf16")
+    row("cfg3 V2 bf16 NHWC batch %d" % Nb, Nb, 4 * F2 + 40 * HW, time_ms(lambda: p.run(s), 3, 10), pk)
+    del nh, p
+    nf = {k: ops.to_nhwc(d[k], torch.float32) for k in ("key", "cur", "scale_map")}
+    p = ops.PreparedAggregate(nf["key"], d["mv"], flow_kind="raw", cur=nf["cur"], scale_map=nf["scale_map"],
+                              weight_mode="logits", logits=d["logits"], layout="nhwc_f32")
+    row("V2 fp32 NHWC batch 64", N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk)
+    del nf, p, d, mvb, lgb
+    torch.cuda.empty_cache()
+
+    # ---- config 4: 1080p -> 68x120 ----
+    H4, W4 = 68, 120
+    N4 = 32 if args.quick else 128
+    d4 = synth(N4, C, H4, W4, 1080, 1920, dev, max_px=96)
+    p = ops.PreparedAggregate(d4["key"], d4["mv"], flow_kind="raw", cur=d4["cur"], scale_map=d4["scale_map"],
+                              weight_mode="logits", logits=d4["logits"])
+    row("cfg4 V2 fp32 NCHW 68x120 batch %d" % N4, N4, 4 * C * H4 * W4 * 4 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk)
+    nh = {k: ops.to_nhwc(d4[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}
+    p = ops.PreparedAggregate(nh["key"], d4["mv"], flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
+                              weight_mode="logits", logits=d4["logits"], layout="nhwc_bf16")
+    row("cfg4 V2 bf16 NHWC 68x120 batch %d" % N4, N4, 4 * C * H4 * W4 * 2 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk)
+
+
+if __name__ == "__main__":
+    main()

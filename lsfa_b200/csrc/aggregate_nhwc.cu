@@ -40,7 +40,7 @@ struct __align__(16) TileRec {
   float w00, w01, w10, w11;   // tap weights, blend weight folded in
   float ww, wc;
   int i00, i01, i10, i11;     // key pixel indices of the taps (in-bounds)
-  int use;                    // bit t: tap t is inside the key plane (read it), bit 8: pixel exists, bit 9: bypass
+  int use;                    // bit 8: pixel exists, bit 9: bypass frame
   int n;                      // frame of the tile
 };
 
@@ -80,9 +80,7 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
         const PixelLoads ld = issue_pixel_loads(P, n, y, x);
         // cosine weights come later (phase 1b); every other mode folds its blend weight here
         const PixelRec t = finish_pixel(P, ld, n, y, x, /*fold=*/P.mode != LSFA_W_COSINE);
-        // taps outside the key plane are not read at all (the reference does not read them);
-        // softmax weights are never 0, so a zero weight here still means "tap invalid or weightless"
-        rec.use |= (t.w00 != 0.f ? 1 : 0) | (t.w01 != 0.f ? 2 : 0) | (t.w10 != 0.f ? 4 : 0) | (t.w11 != 0.f ? 8 : 0);
+        // taps outside the key plane keep weight 0 and a clamped in-bounds index (make_taps)
         rec.w00 = t.w00; rec.w01 = t.w01; rec.w10 = t.w10; rec.w11 = t.w11;
         rec.ww = t.ww; rec.wc = t.wc;
         rec.i00 = t.i00; rec.i01 = t.i01; rec.i10 = t.i10; rec.i11 = t.i11;
@@ -161,78 +159,83 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
 
       if (x < P.W) {
         const int kn = P.key_index ? __ldg(P.key_index + n) : n;
-        const T* kbase = key + (size_t)kn * P.HWk * P.C;
+        const T* kbase = key + (size_t)kn * P.HWk * P.C + lane * L;
 #pragma unroll 1
-        for (int r0 = 0; r0 < kTileH; r0 += 2) {
-          PixelRec t[2];
-          int use[2];
-          size_t obase[2];
-          const T* kp[2][4];
-          float r3[2][3];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const TileRec& rec = cur_recs[(r0 + u) * kTileW + warp];
-            t[u].w00 = rec.w00; t[u].w01 = rec.w01; t[u].w10 = rec.w10; t[u].w11 = rec.w11;
-            t[u].ww = rec.ww; t[u].wc = rec.wc;
-            use[u] = rec.use;
-            const int p = (ty * kTileH + r0 + u) * P.W + x;
-            obase[u] = ((size_t)n * P.HW + p) * P.C;
-            kp[u][0] = kbase + (size_t)rec.i00 * P.C;
-            kp[u][1] = kbase + (size_t)rec.i01 * P.C;
-            kp[u][2] = kbase + (size_t)rec.i10 * P.C;
-            kp[u][3] = kbase + (size_t)rec.i11 * P.C;
-            r3[u][0] = r3[u][1] = r3[u][2] = 0.f;
-            if (HAS_RES && (use[u] & (1 << 8))) {
-              r3[u][0] = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
-              r3[u][1] = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
-              r3[u][2] = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
-            }
+        for (int r = 0; r < kTileH; ++r) {
+          const TileRec& rec = cur_recs[r * kTileW + warp];
+          const int use = rec.use;
+          if (!(use & (1 << 8))) continue;          // row outside the frame (warp-uniform)
+          PixelRec t;
+          t.w00 = rec.w00; t.w01 = rec.w01; t.w10 = rec.w10; t.w11 = rec.w11;
+          t.ww = rec.ww; t.wc = rec.wc;
+          const bool bp = (use & (1 << 9)) != 0;     // ChooseFeat: keep the current feature
+          const int p = (ty * kTileH + r) * P.W + x;
+          const size_t obase = ((size_t)n * P.HW + p) * P.C + lane * L;
+          // invalid taps carry weight 0 and an in-bounds (clamped) index: every load is unconditional
+          const T* k00 = kbase + (size_t)rec.i00 * P.C;
+          const T* k01 = kbase + (size_t)rec.i01 * P.C;
+          const T* k10 = kbase + (size_t)rec.i10 * P.C;
+          const T* k11 = kbase + (size_t)rec.i11 * P.C;
+          const T* ps = scale ? scale + obase : nullptr;
+          const T* pc = has_cur ? cur + obase : nullptr;
+          T* po = out + obase;
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+          if (HAS_RES) {
+            r0 = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
+            r1 = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
+            r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
           }
+          // two channel chunks (2 x 32 lanes x 16 B per stream) in flight: 12 independent loads
 #pragma unroll 1
-          for (int c = lane * L; c < P.C; c += CSTEP) {
+          for (int c = 0; c + lane * L < P.C; c += 2 * CSTEP) {
+            const bool two = c + CSTEP + lane * L < P.C;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            uint4 v[2][4], vs[2], vc[2];
+            uint4 v[2][6];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {      // every load of both rows is issued before any is used
-              const bool live = (use[u] & (1 << 8)) != 0, bp = (use[u] & (1 << 9)) != 0;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) v[u][k] = (live && !bp && (use[u] & (1 << k))) ? ldg_cached_v4(kp[u][k] + c) : z;
-              vs[u] = (live && !bp && scale) ? ldg_stream_v4(scale + obase[u] + c) : z;
-              vc[u] = (live && has_cur) ? ldg_stream_v4(cur + obase[u] + c) : z;
+            for (int h = 0; h < 2; ++h) {
+              const int co = c + h * CSTEP;
+              const bool on = h == 0 || two;
+              v[h][0] = (on && !bp) ? ldg_cached_v4(k00 + co) : z;
+              v[h][1] = (on && !bp) ? ldg_cached_v4(k01 + co) : z;
+              v[h][2] = (on && !bp) ? ldg_cached_v4(k10 + co) : z;
+              v[h][3] = (on && !bp) ? ldg_cached_v4(k11 + co) : z;
+              v[h][4] = (on && !bp && ps) ? ldg_stream_v4(ps + co) : z;
+              v[h][5] = (on && pc) ? ldg_stream_v4(pc + co) : z;
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (!(use[u] & (1 << 8))) continue;
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two) break;
+              const int co = c + h * CSTEP;
               float f00[L], f01[L], f10[L], f11[L], fs[L], fc[L], o[L];
-              V::unpack(v[u][0], f00);
-              V::unpack(v[u][1], f01);
-              V::unpack(v[u][2], f10);
-              V::unpack(v[u][3], f11);
-              V::unpack(vs[u], fs);
-              V::unpack(vc[u], fc);
-              if (use[u] & (1 << 9)) {         // ChooseFeat: keep the current feature
+              V::unpack(v[h][0], f00);
+              V::unpack(v[h][1], f01);
+              V::unpack(v[h][2], f10);
+              V::unpack(v[h][3], f11);
+              V::unpack(v[h][4], fs);
+              V::unpack(v[h][5], fc);
+              if (bp) {
 #pragma unroll
                 for (int i = 0; i < L; ++i) o[i] = fc[i];
               } else {
 #pragma unroll
                 for (int i = 0; i < L; ++i) {
-                  float val = tap_chain(t[u], f00[i], f01[i], f10[i], f11[i]);
+                  float val = tap_chain(t, f00[i], f01[i], f10[i], f11[i]);
                   if (scale) val *= fs[i];
                   if (HAS_RES) {
-                    const float* rw = P.rnet_w + (size_t)(c + i) * 3;
-                    val = fmaf(t[u].ww, rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + c + i),
-                                                  r3[u][0], r3[u][1], r3[u][2]), val);
+                    const float* rw = P.rnet_w + (size_t)(co + lane * L + i) * 3;
+                    val = fmaf(t.ww, rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2),
+                                               __ldg(P.rnet_b + co + lane * L + i), r0, r1, r2), val);
                   }
-                  o[i] = has_cur ? fmaf(t[u].wc, fc[i], val) : val;
+                  o[i] = has_cur ? fmaf(t.wc, fc[i], val) : val;
                 }
               }
               if (P.req_add) {
-                float b[L];
-                V::unpack(*reinterpret_cast<const uint4*>(out + obase[u] + c), b);
+                float bq[L];
+                V::unpack(*reinterpret_cast<const uint4*>(po + co), bq);
 #pragma unroll
-                for (int i = 0; i < L; ++i) o[i] += b[i];
+                for (int i = 0; i < L; ++i) o[i] += bq[i];
               }
-              stg_stream_v4(out + obase[u] + c, V::pack(o));
+              stg_stream_v4(po + co, V::pack(o));
             }
           }
         }

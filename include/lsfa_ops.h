@@ -60,6 +60,9 @@ extern "C" {
 #define LSFA_FLOW_RAW_I32   1   /* raw MV (N,h,w,2) int32 pixels, pooled in-kernel */
 #define LSFA_FLOW_RAW_F32   2   /* raw MV (N,h,w,2) float32 pixels, pooled in-kernel */
 #define LSFA_FLOW_GRID      3   /* normalised grid (N,2,H,W) f32 = output of GridGenerator */
+#define LSFA_FLOW_COVIAR_I32 4  /* MV exactly as coviar returns it: (N,mv_src_h,mv_src_w,2) int32 at the
+                                   video's own resolution; sign/flip (image.py:53-60), the im_scale resize
+                                   (image.py:204) and the stride-16 reduction are all done in-kernel */
 
 /* aggregation of src0 = warp(key)[*scale][+rnet(res)] with src1 = cur */
 #define LSFA_W_NONE   0   /* out = src0                         (SYM:571-576, 678-680) */
@@ -121,6 +124,10 @@ typedef struct LsfaAggArgs {
                                 dynamic work claiming in the all-TMA kernel (NULL = static split).
                                 Contents need no initialisation; one workspace per in-flight call. */
   size_t  workspace_bytes;
+
+  int32_t mv_src_h, mv_src_w; /* LSFA_FLOW_COVIAR_I32: size of the coviar image; mv_h,mv_w = cvRound(src*im_scale) */
+  int32_t mv_negate;         /* LSFA_FLOW_COVIAR_I32: 1 applies motion_vector = -motion_vector (image.py:54) */
+  int32_t mv_hflip;          /* LSFA_FLOW_COVIAR_I32: 1 applies the horizontal flip of image.py:56-60 */
 
   int32_t force_generic;     /* kernel choice (NCHW): 0 auto, 1 generic gather, 2 plane-resident LDG/STG,
                                 3 all-TMA warp-specialised (error if it cannot serve the args) */

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 OK, E_BADARG, E_SHAPE, E_ALIGN, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 REQ_NULL, REQ_WRITE, REQ_INPLACE, REQ_ADD = 0, 1, 2, 3
 POOL_CENTRE2X2, POOL_AVG16 = 0, 1
-FLOW_PREPOOLED, FLOW_RAW_I32, FLOW_RAW_F32, FLOW_GRID = 0, 1, 2, 3
+FLOW_PREPOOLED, FLOW_RAW_I32, FLOW_RAW_F32, FLOW_GRID, FLOW_COVIAR_I32 = 0, 1, 2, 3, 4
 W_NONE, W_ADD, W_MEAN, W_LOGITS, W_COSINE = 0, 1, 2, 3, 4
 LAYOUT_NCHW_F32, LAYOUT_NHWC_F32, LAYOUT_NHWC_BF16 = 0, 1, 2
 
@@ -53,6 +53,7 @@ class LsfaAggArgs(C.Structure):
         ("bypass", C.c_void_p),
         ("out", C.c_void_p), ("req", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("mv_src_h", C.c_int32), ("mv_src_w", C.c_int32), ("mv_negate", C.c_int32), ("mv_hflip", C.c_int32),
         ("force_generic", C.c_int32),
     ]
 

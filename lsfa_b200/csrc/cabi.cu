@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/lsfa_ops.h: argument validation, tiling
 // decisions and kernel launches.  No allocation, no synchronisation, no global mutable
 // state; errors are reported through a thread-local message like MXGetLastError().
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -84,9 +85,18 @@ int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
   if ((long long)a->H * a->W >= (1LL << 24) || (long long)Hk * Wk >= (1LL << 24))
     return fail(LSFA_E_SHAPE, "planes of 2^24 pixels or more are not supported");
   if (!a->key || !a->flow || !a->out) return fail(LSFA_E_BADARG, "key, flow and out are required");
-  if (a->flow_kind < LSFA_FLOW_PREPOOLED || a->flow_kind > LSFA_FLOW_GRID)
+  if (a->flow_kind < LSFA_FLOW_PREPOOLED || a->flow_kind > LSFA_FLOW_COVIAR_I32)
     return fail(LSFA_E_BADARG, "unknown flow_kind %d", a->flow_kind);
-  if (a->flow_kind == LSFA_FLOW_RAW_I32 || a->flow_kind == LSFA_FLOW_RAW_F32) {
+  if (a->flow_kind == LSFA_FLOW_COVIAR_I32) {
+    if (a->mv_src_h <= 0 || a->mv_src_w <= 0) return fail(LSFA_E_SHAPE, "LSFA_FLOW_COVIAR_I32 needs mv_src_h, mv_src_w > 0");
+    if (!(a->im_scale > 0.0)) return fail(LSFA_E_BADARG, "im_scale must be > 0");
+    const long eh = a->im_scale == 1.0 ? a->mv_src_h : lrint((double)a->mv_src_h * a->im_scale);   // cvRound
+    const long ew = a->im_scale == 1.0 ? a->mv_src_w : lrint((double)a->mv_src_w * a->im_scale);
+    if (a->mv_h != eh || a->mv_w != ew)
+      return fail(LSFA_E_SHAPE, "coviar %dx%d at im_scale %g resizes to %ldx%ld, but mv_h,mv_w = %d,%d", a->mv_src_h,
+                  a->mv_src_w, a->im_scale, eh, ew, a->mv_h, a->mv_w);
+  }
+  if (a->flow_kind == LSFA_FLOW_RAW_I32 || a->flow_kind == LSFA_FLOW_RAW_F32 || a->flow_kind == LSFA_FLOW_COVIAR_I32) {
     if (a->mv_h <= 0 || a->mv_w <= 0) return fail(LSFA_E_SHAPE, "raw MV needs mv_h, mv_w > 0");
     if (ceil16(a->mv_h) != a->H || ceil16(a->mv_w) != a->W)
       return fail(LSFA_E_SHAPE, "raw MV %dx%d pools to %dx%d, but H,W = %d,%d", a->mv_h, a->mv_w,
@@ -126,6 +136,9 @@ int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
   P.mv_h = a->mv_h; P.mv_w = a->mv_w;
   P.mv_scale = a->im_scale * (1.0 / 16.0);      // image.py:224: scale = im_scale * rcnn_scale
   P.pool_mode = a->pool_mode;
+  P.src_h = a->mv_src_h; P.src_w = a->mv_src_w;
+  P.inv_scale = a->im_scale > 0.0 ? 1.0 / a->im_scale : 1.0;
+  P.mv_negate = a->mv_negate; P.mv_hflip = a->mv_hflip; P.mv_identity = a->im_scale == 1.0;
   P.scale = a->scale_map; P.res = a->res; P.rnet_w = a->rnet_w; P.rnet_b = a->rnet_b;
   P.cur = a->cur; P.mode = a->weight_mode; P.logits = a->logits;
   P.emb_warp = a->emb_warp; P.emb_cur = a->emb_cur; P.E = a->E;

@@ -29,6 +29,9 @@ struct AggParams {
   const void* flow;
   int mv_h, mv_w;
   double mv_scale;             // im_scale * (1/16)
+  int src_h, src_w;            // LSFA_FLOW_COVIAR_I32: coviar image size (mv_h, mv_w = resized size)
+  double inv_scale;            // 1 / im_scale
+  int mv_negate, mv_hflip, mv_identity;
   int pool_mode;
   const void* scale;
   const float* res;
@@ -183,6 +186,62 @@ __device__ __forceinline__ double pool_cell(const T* __restrict__ img, int h, in
   return __dmul_rn(acc, 1.0 / 256.0);
 }
 
+// ---------------------------------------------------------------------------------------
+// a1+a2 on the fly: one sample of the stage-1 image (sign, h-flip, cv2.resize INTER_LINEAR on
+// float32: horizontal pass then vertical pass, no FMA) computed straight from coviar's int32
+// array; zero beyond the resized image (the pad of image.py:207-215).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void linear_coeff(int d, int sn, double inv_scale, int& s, float& f) {
+  f = (float)(__dsub_rn(__dmul_rn((double)d + 0.5, inv_scale), 0.5));
+  const float fl = floorf(f);
+  s = (int)fl;
+  f = __fsub_rn(f, fl);
+  if (s < 0) { s = 0; f = 0.f; }
+  if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+}
+
+__device__ __forceinline__ float coviar_src(const int* __restrict__ img, int w, int y, int x, int ch,
+                                            int negate, int hflip) {
+  const int xs = hflip ? (w - 1 - x) : x;
+  float v = (float)__ldg(img + ((size_t)y * w + xs) * 2 + ch);
+  if (negate) v = -v;
+  if (hflip && ch == 0) v = -v;
+  return v;
+}
+
+__device__ __forceinline__ float coviar_resized(const int* __restrict__ img, int h, int w, int oy, int ox,
+                                                int ch, double inv_scale, int identity, int negate, int hflip) {
+  if (identity) return coviar_src(img, w, oy, ox, ch, negate, hflip);
+  int sx, sy;
+  float fx, fy;
+  linear_coeff(ox, w, inv_scale, sx, fx);
+  linear_coeff(oy, h, inv_scale, sy, fy);
+  const int sx1 = min(sx + 1, w - 1), sy1 = min(sy + 1, h - 1);
+  const float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
+  const float t0 = __fadd_rn(__fmul_rn(coviar_src(img, w, sy, sx, ch, negate, hflip), a0),
+                             __fmul_rn(coviar_src(img, w, sy, sx1, ch, negate, hflip), fx));
+  const float t1 = __fadd_rn(__fmul_rn(coviar_src(img, w, sy1, sx, ch, negate, hflip), a0),
+                             __fmul_rn(coviar_src(img, w, sy1, sx1, ch, negate, hflip), fx));
+  return __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+}
+
+// pooled (centre 2x2 | avg16) flow component of feature cell (y,x) straight from the coviar image
+__device__ __forceinline__ double coviar_pool_cell(const AggParams& P, const int* __restrict__ img, int y, int x, int ch) {
+  auto at = [&](int ry, int rx) -> double {
+    if (ry >= P.mv_h || rx >= P.mv_w) return 0.0;
+    return (double)coviar_resized(img, P.src_h, P.src_w, ry, rx, ch, P.inv_scale, P.mv_identity, P.mv_negate, P.mv_hflip);
+  };
+  if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+    const double a = at(16 * y + 7, 16 * x + 7), b = at(16 * y + 7, 16 * x + 8);
+    const double c = at(16 * y + 8, 16 * x + 7), d = at(16 * y + 8, 16 * x + 8);
+    return __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d)), 0.25);
+  }
+  double acc = 0.0;
+  for (int r = 0; r < 16; ++r)
+    for (int q = 0; q < 16; ++q) acc = __dadd_rn(acc, at(16 * y + r, 16 * x + q));
+  return __dmul_rn(acc, 1.0 / 256.0);
+}
+
 // flow (feature cells) of output pixel (y,x) of frame n from whatever the caller supplied;
 // returns the normalised grid coordinates gx, gy.
 __device__ __forceinline__ void pixel_grid(const AggParams& P, int n, int y, int x, float& gx,
@@ -199,6 +258,10 @@ __device__ __forceinline__ void pixel_grid(const AggParams& P, int n, int y, int
     const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
     fx = __ldg(f + p);
     fy = __ldg(f + P.HW + p);
+  } else if (P.flow_kind == LSFA_FLOW_COVIAR_I32) {
+    const int* mv = (const int*)P.flow + (size_t)n * P.src_h * P.src_w * 2;
+    fx = (float)__dmul_rn(coviar_pool_cell(P, mv, y, x, 0), P.mv_scale);
+    fy = (float)__dmul_rn(coviar_pool_cell(P, mv, y, x, 1), P.mv_scale);
   } else if (P.flow_kind == LSFA_FLOW_RAW_I32) {
     const int* mv = (const int*)P.flow + (size_t)n * P.mv_h * P.mv_w * 2;
     fx = (float)__dmul_rn(pool_cell(mv, P.mv_h, P.mv_w, 2, y, x, 0, P.pool_mode), P.mv_scale);
@@ -264,7 +327,7 @@ __device__ __forceinline__ PixelLoads issue_pixel_loads(const AggParams& P, int 
     const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
     L.t[0] = __float_as_uint(__ldg(f + p));
     L.t[1] = __float_as_uint(__ldg(f + P.HW + p));
-  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2 && P.flow_kind != LSFA_FLOW_COVIAR_I32) {
     // (x,y) pairs are 8 bytes: one 8-byte load per tap, zero beyond the unpadded image
     const char* img = (const char*)P.flow + (size_t)n * P.mv_h * P.mv_w * 8;
     const int y7 = 16 * y + 7, x7 = 16 * x + 7;
@@ -294,7 +357,7 @@ __device__ __forceinline__ void prefetch_pixel_loads(const AggParams& P, int n, 
     const float* f = (const float*)P.flow + (size_t)n * 2 * P.HW;
     prefetch_l2(f + p);
     prefetch_l2(f + P.HW + p);
-  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
+  } else if (P.pool_mode == LSFA_POOL_CENTRE2X2 && P.flow_kind != LSFA_FLOW_COVIAR_I32) {
     const char* img = (const char*)P.flow + (size_t)n * P.mv_h * P.mv_w * 8;
     const int y7 = 16 * y + 7, x7 = 16 * x + 7;   // x7 and x7+1 share a 32-byte sector unless x7*8 % 32 == 24
     if (y7 < P.mv_h && x7 < P.mv_w) prefetch_l2(img + ((size_t)y7 * P.mv_w + x7) * 8);
@@ -325,6 +388,10 @@ __device__ __forceinline__ PixelRec finish_pixel(const AggParams& P, const Pixel
     if (P.flow_kind == LSFA_FLOW_PREPOOLED) {
       fx = __uint_as_float(L.t[0]);
       fy = __uint_as_float(L.t[1]);
+    } else if (P.flow_kind == LSFA_FLOW_COVIAR_I32) {   // a1+a2 folded in: not prefetched (pre-pass / slow paths)
+      const int* mv = (const int*)P.flow + (size_t)n * P.src_h * P.src_w * 2;
+      fx = (float)__dmul_rn(coviar_pool_cell(P, mv, y, x, 0), P.mv_scale);
+      fy = (float)__dmul_rn(coviar_pool_cell(P, mv, y, x, 1), P.mv_scale);
     } else if (P.pool_mode == LSFA_POOL_CENTRE2X2) {
       const bool i32 = P.flow_kind == LSFA_FLOW_RAW_I32;
       // ((a + b) + (c + d)) * 0.25 * (im_scale / 16), cv2's horizontal-pass-first order

@@ -76,15 +76,6 @@ __global__ void res_pool_kernel(const T* __restrict__ res, float* __restrict__ o
 // float32 (image.py:204): horizontal pass then vertical pass, float32, no FMA; coefficient
 // fx = (float)((d+0.5)/im_scale - 0.5), floor/frac split, edge rules of cv::resize.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void linear_coeff(int d, int sn, double inv_scale, int& s, float& f) {
-  f = (float)(__dsub_rn(__dmul_rn((double)d + 0.5, inv_scale), 0.5));
-  const float fl = floorf(f);
-  s = (int)fl;
-  f = __fsub_rn(f, fl);
-  if (s < 0) { s = 0; f = 0.f; }
-  if (s >= sn - 1) { s = sn - 1; f = 0.f; }
-}
-
 __global__ void mv_prepare_kernel(const int* __restrict__ in, float* __restrict__ out, int N,
                                   int h, int w, int oh, int ow, double inv_scale, int identity,
                                   int negate, int hflip) {
@@ -95,32 +86,9 @@ __global__ void mv_prepare_kernel(const int* __restrict__ in, float* __restrict_
     const int oy = (int)((i / ow) % oh);
     const int n = (int)(i / ((long long)ow * oh));
     const int* img = in + (size_t)n * h * w * 2;
-    // source sample after a1 (sign, flip), as float32
-    auto src = [&](int y, int x, int ch) -> float {
-      const int xs = hflip ? (w - 1 - x) : x;
-      float v = (float)__ldg(img + ((size_t)y * w + xs) * 2 + ch);
-      if (negate) v = -v;
-      if (hflip && ch == 0) v = -v;
-      return v;
-    };
     float r[2];
-    if (identity) {
-      r[0] = src(oy, ox, 0);
-      r[1] = src(oy, ox, 1);
-    } else {
-      int sx, sy;
-      float fx, fy;
-      linear_coeff(ox, w, inv_scale, sx, fx);
-      linear_coeff(oy, h, inv_scale, sy, fy);
-      const int sx1 = min(sx + 1, w - 1), sy1 = min(sy + 1, h - 1);
-      const float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const float t0 = __fadd_rn(__fmul_rn(src(sy, sx, ch), a0), __fmul_rn(src(sy, sx1, ch), fx));
-        const float t1 = __fadd_rn(__fmul_rn(src(sy1, sx, ch), a0), __fmul_rn(src(sy1, sx1, ch), fx));
-        r[ch] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
-      }
-    }
+    r[0] = coviar_resized(img, h, w, oy, ox, 0, inv_scale, identity, negate, hflip);
+    r[1] = coviar_resized(img, h, w, oy, ox, 1, inv_scale, identity, negate, hflip);
     reinterpret_cast<float2*>(out)[i] = make_float2(r[0], r[1]);
   }
 }

@@ -209,7 +209,7 @@ def _feature_dims(t: torch.Tensor, layout: int):
 
 def _build_args(key, flow, *, cur=None, scale_map=None, res=None, rnet_w=None, rnet_b=None,
                 weight_mode="none", logits=None, emb_warp=None, emb_cur=None, bypass=None,
-                key_index=None, flow_kind="flow", im_scale=1.0, pool_mode="centre2x2",
+                key_index=None, flow_kind="flow", im_scale=1.0, pool_mode="centre2x2", negate=True, flipped=False,
                 layout="nchw", out=None, req="write", workspace=None, force_generic=False):
     lay = _LAYOUT[layout] if isinstance(layout, str) else layout
     fdt = _feat_dtype(lay)
@@ -236,8 +236,18 @@ def _build_args(key, flow, *, cur=None, scale_map=None, res=None, rnet_w=None, r
             fk = A.FLOW_RAW_F32
         else:
             raise TypeError("raw mv must be int32 or float32")
+    elif flow_kind == "coviar":
+        # the MV exactly as coviar_py2.load(..., 1, True) returns it (image.py:53): sign, flip and the
+        # im_scale resize of image.py:54-60,204 happen in the kernel
+        _dev(flow, "flow (coviar mv)", torch.int32)
+        if flow.dim() != 4 or flow.shape[3] != 2:
+            raise ValueError("coviar mv must be (N,h,w,2) int32, got %s" % (tuple(flow.shape),))
+        N, src_h, src_w, _ = flow.shape
+        mv_h, mv_w = (src_h, src_w) if im_scale == 1.0 else (cv_round(src_h * im_scale), cv_round(src_w * im_scale))
+        H, W = _ceil16(mv_h), _ceil16(mv_w)
+        fk = A.FLOW_COVIAR_I32
     else:
-        raise ValueError("flow_kind must be 'flow', 'grid' or 'raw'")
+        raise ValueError("flow_kind must be 'flow', 'grid', 'raw' or 'coviar'")
     keep.append(flow)
 
     if key_index is not None:
@@ -312,6 +322,9 @@ def _build_args(key, flow, *, cur=None, scale_map=None, res=None, rnet_w=None, r
         cur=_ptr(cur), weight_mode=wm, logits=_ptr(logits), emb_warp=_ptr(emb_warp),
         emb_cur=_ptr(emb_cur), E=E, bypass=_ptr(bypass), out=_ptr(out), req=rq,
         force_generic=int(force_generic))
+    if fk == A.FLOW_COVIAR_I32:
+        args.mv_src_h, args.mv_src_w = src_h, src_w
+        args.mv_negate, args.mv_hflip = int(bool(negate)), int(bool(flipped))
     lib = A.load()
     need = lib.lsfa_warp_scale_aggregate_workspace_bytes(args)
     if workspace is False and wm != A.W_COSINE:
@@ -333,7 +346,7 @@ def warp_scale_aggregate(key, flow, **kw) -> torch.Tensor:
 
     Keyword arguments: cur, scale_map, res, rnet_w, rnet_b, weight_mode ('none'|'add'|'mean'|
     'logits'|'cosine'), logits (N,2,H,W), emb_warp, emb_cur, bypass (N,) uint8, key_index (N,)
-    int32, flow_kind ('flow'|'grid'|'raw'), im_scale, pool_mode, layout ('nchw'|'nhwc_f32'|
+    int32, flow_kind ('flow'|'grid'|'raw'|'coviar'), im_scale, pool_mode, negate, flipped, layout ('nchw'|'nhwc_f32'|
     'nhwc_bf16'), out, req, workspace, force_generic.
     """
     args, out, _keep = _build_args(key, flow, **kw)

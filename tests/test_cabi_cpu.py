@@ -79,6 +79,9 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.lsfa_grid_generator_warp_f32(16, 16, 0, 4, 4, None) == A.E_SHAPE
     assert lib.lsfa_bilinear_sampler_f32(16, 16, 16, 1, 1, 0, 4, 4, 4, 1, None) == A.E_SHAPE
     assert lib.lsfa_bilinear_sampler_f32(16, 16, 16, 1, 1, 4, 4, 4, 4, 9, None) == A.E_BADARG   # bad req
+    a = A.new_args(N=1, C=8, H=38, W=63, req=A.REQ_WRITE, key=16, flow=16, out=16, flow_kind=A.FLOW_COVIAR_I32,
+                   mv_src_h=720, mv_src_w=1280, mv_h=562, mv_w=999, im_scale=0.78125)
+    assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_SHAPE             # 1280*0.78125 rounds to 1000, not 999
     assert lib.lsfa_unfused_chain_num_launches() == 9
 
 

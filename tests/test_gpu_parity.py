@@ -297,6 +297,36 @@ def test_all_tma_static_and_dynamic_split_agree(ops, cuda):
     assert_close_f32(a, oracle_fused(d, O.W_LOGITS), scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="dyn")
 
 
+@pytest.mark.parametrize("src_hw,scale", [((360, 480), 600 / 360.0), ((480, 854), 1.0), ((720, 1280), 0.78125), ((203, 317), 1.25)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_coviar_front_end_folded_into_the_kernel(ops, cuda, src_hw, scale, flip):
+    """flow_kind='coviar' = image.py:53-60 (sign, flip) + :204 (cv2 resize by im_scale) + :207-228 inside the
+    fused op.  Bit-identical to running mv_prepare and mv_pool first, and inside the fp32 gate vs the oracle."""
+    h0, w0 = src_hw
+    rng = np.random.default_rng(h0)
+    raw = O.synth_raw_mv(rng, 2, h0, w0, 24)                       # what coviar returns (before the sign flip)
+    stage1 = np.stack([O.resize_linear_f32(O.mv_sign_flip(r, flip), scale) for r in raw])
+    flow = O.mv_pool(stage1, scale)
+    N, _, H, W = flow.shape
+    C = 16
+    key = O.synth_features(rng, (N, C, H, W)); cur = O.synth_features(rng, (N, C, H, W))
+    sm = O.synth_scale_map(rng, (N, C, H, W)); lg = rng.standard_normal((N, 2, H, W), dtype=np.float32)
+    want = O.warp_scale_aggregate(key, flow, cur=cur, scale_map=sm, weight_mode=O.W_LOGITS, logits=lg)
+    kw = dict(cur=dev(cur, cuda), scale_map=dev(sm, cuda), weight_mode="logits", logits=dev(lg, cuda))
+    two_step = ops.warp_scale_aggregate(dev(key, cuda), ops.mv_prepare(dev(raw, cuda), scale, True, flip),
+                                        flow_kind="raw", im_scale=scale, **kw)
+    for fg in (0, 1, 2):
+        got = ops.warp_scale_aggregate(dev(key, cuda), dev(raw, cuda), flow_kind="coviar", im_scale=scale,
+                                       negate=True, flipped=flip, force_generic=fg, **kw)
+        assert torch.equal(got, two_step), "kernel choice %d" % fg
+    assert_close_f32(host(got), want, scale=max(np.abs(key).max(), np.abs(cur).max()), what="coviar")
+    nh = lambda a: ops.to_nhwc(dev(a, cuda))  # noqa: E731
+    got_nhwc = ops.to_nchw(ops.warp_scale_aggregate(nh(key), dev(raw, cuda), flow_kind="coviar", im_scale=scale, negate=True,
+                                                    flipped=flip, layout="nhwc_f32", cur=nh(cur), scale_map=nh(sm),
+                                                    weight_mode="logits", logits=dev(lg, cuda)))
+    assert torch.equal(got_nhwc, two_step)
+
+
 def test_shared_key_feature_tile_as(ops, cuda):
     """get_batch_test_symbol (SYM:675-680): one key feature, many frames (tile_as -> key_index)."""
     d = make_case(9, 5, 32, 38, 63, shared_key=True)

@@ -10,7 +10,7 @@
 // the key feature's reuse is served by the 126 MB L2.  fp32 arithmetic throughout.
 // The cosine-embedding weights (Fgfa_net) are computed in the same pass with warp-shuffle
 // reductions, so this layout needs no workspace and no second kernel.
-#include "lsfa_device.cuh"
+#include "aggregate_nchw_plane.cuh"   // PlaneVariant: the same compile-time variants as the NCHW kernels
 
 namespace lsfa {
 
@@ -44,9 +44,11 @@ struct __align__(16) TileRec {
   int n;                      // frame of the tile
 };
 
-template <typename T, bool HAS_RES>
+template <typename T, int VAR>
 __global__ void __launch_bounds__(kNhwcTileThreads, 2)
 agg_nhwc_kernel(const __grid_constant__ AggParams P) {
+  constexpr bool RT = VAR == kVarRuntime;
+  constexpr bool HAS_RES = RT || VAR == kVarResCur;   // RT: decided at run time below
   using V = Vec16<T>;
   constexpr int L = V::kLanes;        // channels per 16-byte vector
   constexpr int CSTEP = 32 * L;       // channels per warp pass
@@ -56,7 +58,10 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
   const T* __restrict__ scale = static_cast<const T*>(P.scale);
   const T* __restrict__ cur = static_cast<const T*>(P.cur);
   T* __restrict__ out = static_cast<T*>(P.out);
-  const bool has_cur = P.mode != LSFA_W_NONE;
+  const bool has_cur = RT ? (P.mode != LSFA_W_NONE) : (VAR == kVarScaleCur || VAR == kVarResCur);
+  const bool has_scale = RT ? (scale != nullptr) : (VAR == kVarScale || VAR == kVarScaleCur);
+  const bool has_res = RT ? (P.res != nullptr) : (VAR == kVarResCur);
+  const bool req_add = RT ? (P.req_add != 0) : false;
   const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kTileH - 1) / kTileH;
   const long long tiles = (long long)P.N * tiles_x * tiles_y;
 
@@ -169,6 +174,9 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
           t.w00 = rec.w00; t.w01 = rec.w01; t.w10 = rec.w10; t.w11 = rec.w11;
           t.ww = rec.ww; t.wc = rec.wc;
           const bool bp = (use & (1 << 9)) != 0;     // ChooseFeat: keep the current feature
+          const f32x2 w00p = pair2(t.w00, t.w00), w01p = pair2(t.w01, t.w01), w10p = pair2(t.w10, t.w10),
+                      w11p = pair2(t.w11, t.w11), wcp = pair2(t.wc, t.wc), wwp = pair2(t.ww, t.ww);
+          (void)wwp;
           const int p = (ty * kTileH + r) * P.W + x;
           const size_t obase = ((size_t)n * P.HW + p) * P.C + lane * L;
           // invalid taps carry weight 0 and an in-bounds (clamped) index: every load is unconditional
@@ -176,66 +184,75 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
           const T* k01 = kbase + (size_t)rec.i01 * P.C;
           const T* k10 = kbase + (size_t)rec.i10 * P.C;
           const T* k11 = kbase + (size_t)rec.i11 * P.C;
-          const T* ps = scale ? scale + obase : nullptr;
-          const T* pc = has_cur ? cur + obase : nullptr;
+          const T* ps = scale + obase;     // only dereferenced when has_scale / has_cur
+          const T* pc = cur + obase;
           T* po = out + obase;
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-          if (HAS_RES) {
+          if (HAS_RES && has_res) {
             r0 = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
             r1 = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
             r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
           }
           // two channel chunks (2 x 32 lanes x 16 B per stream) in flight: 12 independent loads
 #pragma unroll 1
-          for (int c = 0; c + lane * L < P.C; c += 2 * CSTEP) {
+          for (int c = 0; c + lane * L < P.C; c += 2 * CSTEP, k00 += 2 * CSTEP, k01 += 2 * CSTEP, k10 += 2 * CSTEP,
+                   k11 += 2 * CSTEP, ps += 2 * CSTEP, pc += 2 * CSTEP, po += 2 * CSTEP) {
             const bool two = c + CSTEP + lane * L < P.C;
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint4 v[2][6];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int co = c + h * CSTEP;
+              const int co = h * CSTEP;            // compile-time offset from the running pointers
               const bool on = h == 0 || two;
               v[h][0] = (on && !bp) ? ldg_cached_v4(k00 + co) : z;
               v[h][1] = (on && !bp) ? ldg_cached_v4(k01 + co) : z;
               v[h][2] = (on && !bp) ? ldg_cached_v4(k10 + co) : z;
               v[h][3] = (on && !bp) ? ldg_cached_v4(k11 + co) : z;
-              v[h][4] = (on && !bp && ps) ? ldg_stream_v4(ps + co) : z;
-              v[h][5] = (on && pc) ? ldg_stream_v4(pc + co) : z;
+              v[h][4] = (on && !bp && has_scale) ? ldg_stream_v4(ps + co) : z;
+              v[h][5] = (on && has_cur) ? ldg_stream_v4(pc + co) : z;
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (h == 1 && !two) break;
-              const int co = c + h * CSTEP;
-              float f00[L], f01[L], f10[L], f11[L], fs[L], fc[L], o[L];
-              V::unpack(v[h][0], f00);
-              V::unpack(v[h][1], f01);
-              V::unpack(v[h][2], f10);
-              V::unpack(v[h][3], f11);
-              V::unpack(v[h][4], fs);
-              V::unpack(v[h][5], fc);
+              const int co = h * CSTEP;
+              // packed dual-fp32 math (FFMA2/FMUL2): half the FP instructions, same bits as scalar fmaf
+              constexpr int H2 = L / 2;
+              f32x2 f00[H2], f01[H2], f10[H2], f11[H2], fs[H2], fc[H2], o[H2];
+              V::unpack2(v[h][0], f00);
+              V::unpack2(v[h][1], f01);
+              V::unpack2(v[h][2], f10);
+              V::unpack2(v[h][3], f11);
+              V::unpack2(v[h][4], fs);
+              V::unpack2(v[h][5], fc);
               if (bp) {
 #pragma unroll
-                for (int i = 0; i < L; ++i) o[i] = fc[i];
+                for (int i = 0; i < H2; ++i) o[i] = fc[i];
               } else {
 #pragma unroll
-                for (int i = 0; i < L; ++i) {
-                  float val = tap_chain(t, f00[i], f01[i], f10[i], f11[i]);
-                  if (scale) val *= fs[i];
-                  if (HAS_RES) {
-                    const float* rw = P.rnet_w + (size_t)(co + lane * L + i) * 3;
-                    val = fmaf(t.ww, rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2),
-                                               __ldg(P.rnet_b + co + lane * L + i), r0, r1, r2), val);
+                for (int i = 0; i < H2; ++i) {
+                  f32x2 val = mul2(w00p, f00[i]);
+                  val = fma2(w01p, f01[i], val);
+                  val = fma2(w10p, f10[i], val);
+                  val = fma2(w11p, f11[i], val);
+                  if (has_scale) val = mul2(val, fs[i]);
+                  if (HAS_RES && has_res) {
+                    const int ch = c + co + lane * L + 2 * i;
+                    const float* rw = P.rnet_w + (size_t)ch * 3;
+                    const float ra = rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + ch), r0, r1, r2);
+                    const float rb = rnet_term(__ldg(rw + 3), __ldg(rw + 4), __ldg(rw + 5), __ldg(P.rnet_b + ch + 1), r0, r1, r2);
+                    val = fma2(wwp, pair2(ra, rb), val);
                   }
-                  o[i] = has_cur ? fmaf(t.wc, fc[i], val) : val;
+                  o[i] = has_cur ? fma2(wcp, fc[i], val) : val;
                 }
               }
-              if (P.req_add) {
-                float bq[L];
-                V::unpack(*reinterpret_cast<const uint4*>(po + co), bq);
+              if (req_add) {
+                f32x2 bq[H2];
+                V::unpack2(*reinterpret_cast<const uint4*>(po + co), bq);
+                const f32x2 one = pair2(1.0f, 1.0f);
 #pragma unroll
-                for (int i = 0; i < L; ++i) o[i] += bq[i];
+                for (int i = 0; i < H2; ++i) o[i] = fma2(one, bq[i], o[i]);
               }
-              stg_stream_v4(po + co, V::pack(o));
+              stg_stream_v4(po + co, V::pack2(o));
             }
           }
         }
@@ -301,11 +318,22 @@ cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long grid = (long long)sms * 2;    // persistent: 2 resident CTAs per SM
   if (grid > tiles) grid = tiles;
-  const bool res = P.res != nullptr;
-  if (bf16 && res) agg_nhwc_kernel<__nv_bfloat16, true><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);
-  else if (bf16) agg_nhwc_kernel<__nv_bfloat16, false><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);
-  else if (res) agg_nhwc_kernel<float, true><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);
-  else agg_nhwc_kernel<float, false><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);
+  const bool has_scale = P.scale != nullptr, has_cur = P.mode != LSFA_W_NONE, has_res = P.res != nullptr;
+  int var = kVarRuntime;
+  if (!P.req_add) {
+    if (!has_scale && !has_cur && !has_res) var = kVarWarpOnly;
+    else if (has_scale && !has_cur && !has_res) var = kVarScale;
+    else if (has_scale && has_cur && !has_res) var = kVarScaleCur;
+    else if (!has_scale && has_cur && has_res) var = kVarResCur;
+  }
+#define LSFA_NHWC_CASE(V)                                                                              \
+  if (var == V) {                                                                                      \
+    if (bf16) agg_nhwc_kernel<__nv_bfloat16, V><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);       \
+    else agg_nhwc_kernel<float, V><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);                    \
+  }
+  LSFA_NHWC_CASE(kVarRuntime) LSFA_NHWC_CASE(kVarWarpOnly) LSFA_NHWC_CASE(kVarScale)
+  LSFA_NHWC_CASE(kVarScaleCur) LSFA_NHWC_CASE(kVarResCur)
+#undef LSFA_NHWC_CASE
   return cudaPeekAtLastError();
 }
 

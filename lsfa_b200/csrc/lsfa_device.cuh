@@ -550,6 +550,28 @@ __device__ __forceinline__ void stg_stream_v4(void* p, uint4 v) {
                : "memory");
 }
 
+// Packed dual-fp32 arithmetic (Blackwell FFMA2/FMUL2: one instruction, two IEEE fp32 results -
+// bit-identical to two scalar fmaf/fmul).  A pair lives in a 64-bit register: lo = element 2i.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pair2(float lo, float hi) {
+  f32x2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpair2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // 16-byte vector <-> float lanes for the NHWC kernels
 template <typename T>
 struct Vec16;
@@ -565,6 +587,17 @@ struct Vec16<float> {
   __device__ static __forceinline__ uint4 pack(const float* f) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
                       __float_as_uint(f[3]));
+  }
+  // pair form: kLanes/2 packed f32x2
+  __device__ static __forceinline__ void unpack2(const uint4& v, f32x2* f) {
+    f[0] = pair2(__uint_as_float(v.x), __uint_as_float(v.y));
+    f[1] = pair2(__uint_as_float(v.z), __uint_as_float(v.w));
+  }
+  __device__ static __forceinline__ uint4 pack2(const f32x2* f) {
+    float a, b, c, d;
+    unpair2(f[0], a, b);
+    unpair2(f[1], c, d);
+    return make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
   }
 };
 template <>
@@ -583,6 +616,22 @@ struct Vec16<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      u[i] = *reinterpret_cast<unsigned*>(&h);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+  }
+  __device__ static __forceinline__ void unpack2(const uint4& v, f32x2* f) {
+    const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = pair2(__uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+  }
+  __device__ static __forceinline__ uint4 pack2(const f32x2* f) {
+    unsigned u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float lo, hi;
+      unpair2(f[i], lo, hi);
+      __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
       u[i] = *reinterpret_cast<unsigned*>(&h);
     }
     return make_uint4(u[0], u[1], u[2], u[3]);

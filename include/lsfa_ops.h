@@ -205,6 +205,22 @@ LSFA_API int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat
                                   const uint8_t* eq_flag, float* out, int N, long long per_frame,
                                   void* stream);
 
+/* Upstream of the path: coviar's accumulated MV field and residual for N GOPs at
+ * once - external/data_loader_py2/coviar_data_loader.c:71-177 (create_and_load_mv_residual, accumulate=1)
+ * with the identity initialisation of :318-328.
+ * mvs: (N,T,M,6) int32 = per decoded P-frame t (1..T in decode order) up to M motion vectors, each
+ *      {w, h, src_x, src_y, dst_x, dst_y} of FFmpeg's AVMotionVector in list order; counts (N,T) = how
+ *      many are valid.  mv_out (N,height,width,2) int32 = what coviar_py2.load(.., 1, True) returns.
+ * workspace: lsfa_mv_accumulate_workspace_bytes(N,height,width) bytes, no initialisation needed. */
+LSFA_API size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width);
+LSFA_API int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height,
+                                    int width, int32_t* mv_out, void* workspace, size_t workspace_bytes,
+                                    void* stream);
+/* residual of coviar_data_loader.c:141-175: res = cur - iframe[(x,y) - mv]; frames (N,height,width,3) uint8
+ * BGR, mv the accumulated field above, res (N,height,width,3) int32. */
+LSFA_API int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res,
+                                     int N, int height, int width, void* stream);
+
 /* layout helpers for the harness: NCHW f32 <-> NHWC {f32,bf16} */
 LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout,
                       void* stream);

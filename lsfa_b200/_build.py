@@ -15,8 +15,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblsfa_b200.so")
-SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu",
-           "plane_var0.cu", "plane_var1.cu", "plane_var2.cu", "plane_var3.cu", "plane_var4.cu",
+SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu", "coviar_accumulate.cu",
+           "plane_var0.cu", "plane_var3.cu",
            "tma_var1.cu", "tma_var2.cu", "tma_var3.cu", "tma_var4.cu"]
 HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"), os.path.join(CSRC, "aggregate_nchw_plane.cuh"),
            os.path.join(CSRC, "plane_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma.cuh"),

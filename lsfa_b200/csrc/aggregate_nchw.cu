@@ -154,8 +154,8 @@ bool plan_plane_kernel(AggParams& P, size_t* smem_out) {
   if (((long long)P.C * P.HWk) % 4) return false;      // every frame's planes stay 16 B aligned
   // pixel slots per thread: 8 only for the lean variants at K=2 (register budget), else <= 5
   const bool lean = !P.req_add && P.res == nullptr;
-  const int n_opt = (K == 2 && lean) ? 5 : 4;
-  const int ppt_options[5] = {1, 2, 3, 5, 8};
+  const int n_opt = (K == 2 && lean) ? 4 : 3;
+  const int ppt_options[4] = {1, 3, 5, 8};
   int ppt = ppt_options[n_opt - 1];
   for (int i = n_opt - 1; i >= 0; --i)
     if ((long long)ppt_options[i] * kPlaneThreads >= P.HW) ppt = ppt_options[i];
@@ -178,12 +178,10 @@ cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t 
   long long grid = sm_count();
   if (grid > P.items) grid = P.items;
   const bool has_scale = P.scale != nullptr, has_cur = P.mode != LSFA_W_NONE, has_res = P.res != nullptr;
-  if (!P.req_add) {
-    if (!has_scale && !has_cur && !has_res) return launch_plane_variant<kVarWarpOnly>(P, smem, (int)grid, st);
-    if (has_scale && !has_cur && !has_res) return launch_plane_variant<kVarScale>(P, smem, (int)grid, st);
-    if (has_scale && has_cur && !has_res) return launch_plane_variant<kVarScaleCur>(P, smem, (int)grid, st);
-    if (!has_scale && has_cur && has_res) return launch_plane_variant<kVarResCur>(P, smem, (int)grid, st);
-  }
+  // this kernel is the fallback of the all-TMA one: only the run-time-flag form and the key-frame
+  // blend (kept specialised for the LDG/STG-vs-TMA ablation) are instantiated
+  if (!P.req_add && has_scale && has_cur && !has_res) return launch_plane_variant<kVarScaleCur>(P, smem, (int)grid, st);
+  (void)has_res;
   return launch_plane_variant<kVarRuntime>(P, smem, (int)grid, st);
 }
 
@@ -243,13 +241,13 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   if (((long long)P.C * P.HW) % 4 || ((long long)P.C * P.HWk) % 4) return false;
   // pixel slots per consumer thread; planes beyond 9*480 pixels are cut into balanced parts,
   // which needs every plane slice 16-byte aligned (HW % 4 == 0)
-  const int ppt_options[6] = {1, 2, 3, 5, 7, 9};
+  const int ppt_options[4] = {1, 3, 5, 9};
   const int max_part = 9 * kTmaConsumers;
   const int parts = (P.HW + max_part - 1) / max_part;
   if (parts > 1 && (P.HW % 4)) return false;
   const int per_part = (P.HW + parts - 1) / parts;
   int ppt = 9;
-  for (int i = 5; i >= 0; --i)
+  for (int i = 3; i >= 0; --i)
     if ((long long)ppt_options[i] * kTmaConsumers >= per_part) ppt = ppt_options[i];
   const int part_pix = ppt * kTmaConsumers;
   if ((long long)part_pix * (parts - 1) >= P.HW) return false;   // every part must be non-empty

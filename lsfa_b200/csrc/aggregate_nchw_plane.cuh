@@ -275,8 +275,7 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
 template <int VAR>
 cudaError_t launch_plane_variant(const AggParams& P, size_t smem, int grid, cudaStream_t st);
 
-#define LSFA_PLANE_FOREACH_KP(X) \
-  X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 8) X(4, 1) X(4, 2) X(4, 3) X(4, 5) X(4, 8)
+#define LSFA_PLANE_FOREACH_KP(X) X(2, 1) X(2, 3) X(2, 5) X(2, 8) X(4, 1) X(4, 3) X(4, 5)
 
 #define LSFA_PLANE_LAUNCH(VAR, KK, PP)                                                            \
   if (P.K == KK && ppt == PP) {                                                                   \

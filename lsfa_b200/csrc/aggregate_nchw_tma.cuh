@@ -385,8 +385,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
 template <int VAR>
 cudaError_t launch_tma_variant(const AggParams& P, size_t smem, int grid, cudaStream_t st);
 
-#define LSFA_TMA_FOREACH_KP(X) \
-  X(1, 1) X(1, 2) X(1, 3) X(1, 5) X(1, 7) X(1, 9) X(2, 1) X(2, 2) X(2, 3) X(2, 5) X(2, 7) X(2, 9)
+#define LSFA_TMA_FOREACH_KP(X) X(1, 1) X(1, 3) X(1, 5) X(1, 9) X(2, 1) X(2, 3) X(2, 5) X(2, 9)
 
 #define LSFA_TMA_LAUNCH(VAR, KK, PP)                                                              \
   if (P.K == KK && ppt == PP) {                                                                   \

@@ -41,6 +41,11 @@ cudaError_t launch_unfused_chain(const float* key, const float* flow, const floa
 int unfused_chain_launches();
 cudaError_t launch_choose_feat(const float* a, const float* b, const unsigned char* flag, float* o,
                                long long per_frame, long long total, cudaStream_t st);
+// coviar_accumulate.cu
+cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
+                                 int* mv_out, void* workspace, cudaStream_t st);
+cudaError_t launch_coviar_residual(const unsigned char* iframe, const unsigned char* cur, const int* mv, int* res, int N,
+                                   int height, int width, cudaStream_t st);
 }  // namespace lsfa
 
 namespace {
@@ -359,6 +364,32 @@ int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat_prop, co
   return cuda_result(lsfa::launch_choose_feat(conv_feat, conv_feat_prop, eq_flag, out, per_frame,
                                               (long long)N * per_frame, as_stream(stream)),
                      "choose_feat launch");
+}
+
+size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width) {
+  if (N <= 0 || height <= 0 || width <= 0) return 0;
+  return (size_t)N * height * width * (2 * 8 + 4);      // two (x,y) int2 fields + the owner map
+}
+
+int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height, int width,
+                           int32_t* mv_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!mvs || !counts || !mv_out || !workspace) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || T < 0 || M <= 0 || height <= 0 || width <= 0 || N > 65535) return fail(LSFA_E_SHAPE, "bad dims");
+  if (workspace_bytes < lsfa_mv_accumulate_workspace_bytes(N, height, width))
+    return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", lsfa_mv_accumulate_workspace_bytes(N, height, width));
+  if ((reinterpret_cast<uintptr_t>(workspace) % 8) || (reinterpret_cast<uintptr_t>(mv_out) % 8))
+    return fail(LSFA_E_ALIGN, "workspace and mv_out must be 8-byte aligned");
+  return cuda_result(lsfa::launch_mv_accumulate(mvs, counts, N, T, M, height, width, mv_out, workspace, as_stream(stream)),
+                     "mv_accumulate launch");
+}
+
+int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res, int N, int height,
+                            int width, void* stream) {
+  if (!iframe || !cur || !mv || !res) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || height <= 0 || width <= 0) return fail(LSFA_E_SHAPE, "bad dims");
+  if (reinterpret_cast<uintptr_t>(mv) % 8) return fail(LSFA_E_ALIGN, "mv must be 8-byte aligned");
+  return cuda_result(lsfa::launch_coviar_residual(iframe, cur, mv, res, N, height, width, as_stream(stream)),
+                     "coviar_residual launch");
 }
 
 int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout, void* stream) {

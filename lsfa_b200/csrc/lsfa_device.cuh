@@ -181,7 +181,9 @@ __device__ __forceinline__ double pool_cell(const T* __restrict__ img, int h, in
     return __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d)), 0.25);
   }
   double acc = 0.0;
+#pragma unroll 1
   for (int r = 0; r < 16; ++r)
+#pragma unroll 1
     for (int q = 0; q < 16; ++q) acc = __dadd_rn(acc, raw_at(img, h, w, nch, y0 + r, x0 + q, ch));
   return __dmul_rn(acc, 1.0 / 256.0);
 }
@@ -237,7 +239,9 @@ __device__ __forceinline__ double coviar_pool_cell(const AggParams& P, const int
     return __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d)), 0.25);
   }
   double acc = 0.0;
+#pragma unroll 1
   for (int r = 0; r < 16; ++r)
+#pragma unroll 1
     for (int q = 0; q < 16; ++q) acc = __dadd_rn(acc, at(16 * y + r, 16 * x + q));
   return __dmul_rn(acc, 1.0 / 256.0);
 }

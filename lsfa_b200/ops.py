@@ -27,7 +27,7 @@ from . import _cabi as A
 __all__ = [
     "GridGenerator", "BilinearSampler", "mv_prepare", "mv_pool", "res_pool", "transform_mv_res",
     "sampler_coords", "warp_scale_aggregate", "cur_frame_path", "Nq_aggregate", "Fgfa_aggregate",
-    "mean_aggregate", "ChooseFeat", "tile_as", "cosine_logits", "unfused_chain", "to_nhwc",
+    "mean_aggregate", "ChooseFeat", "tile_as", "cosine_logits", "unfused_chain", "mv_accumulate", "coviar_residual", "to_nhwc",
     "to_nchw", "num_launches",
 ]
 
@@ -451,6 +451,37 @@ def unfused_chain(key, flow, scale_map, cur, logits, tmp=None) -> torch.Tensor:
                                                  cur.data_ptr(), logits.data_ptr(), out.data_ptr(),
                                                  tmp.data_ptr(), N, Cc, H, W, _stream()))
     return out
+
+
+def mv_accumulate(mvs: torch.Tensor, counts: torch.Tensor, height: int, width: int, workspace=None) -> torch.Tensor:
+    """coviar's accumulated MV field (coviar_data_loader.c:71-139, accumulate=1) for N GOPs at once.
+    mvs (N,T,M,6) int32 {w,h,src_x,src_y,dst_x,dst_y} per P-frame in list order, counts (N,T) int32
+    -> (N,height,width,2) int32, the array coviar_py2.load(video, gop, pos=T, 1, True) returns."""
+    _dev(mvs, "mvs", torch.int32)
+    _dev(counts, "counts", torch.int32)
+    if mvs.dim() != 4 or mvs.shape[3] != 6 or tuple(counts.shape) != tuple(mvs.shape[:2]):
+        raise ValueError("mvs must be (N,T,M,6) and counts (N,T)")
+    N, T, M, _ = mvs.shape
+    lib = A.load()
+    need = lib.lsfa_mv_accumulate_workspace_bytes(N, height, width)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=mvs.device)
+    out = torch.empty((N, height, width, 2), dtype=torch.int32, device=mvs.device)
+    A.check(lib.lsfa_mv_accumulate_i32(mvs.data_ptr(), counts.data_ptr(), N, T, M, height, width, out.data_ptr(),
+                                       workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()))
+    return out
+
+
+def coviar_residual(iframe: torch.Tensor, cur: torch.Tensor, mv: torch.Tensor) -> torch.Tensor:
+    """coviar_data_loader.c:141-175: res = cur - iframe[(x,y) - mv]; frames (N,h,w,3) uint8, mv (N,h,w,2) int32."""
+    _dev(iframe, "iframe", torch.uint8)
+    _dev(cur, "cur", torch.uint8)
+    _dev(mv, "mv", torch.int32)
+    N, h, w, _ = cur.shape
+    res = torch.empty((N, h, w, 3), dtype=torch.int32, device=cur.device)
+    A.check(A.load().lsfa_coviar_residual_u8(iframe.data_ptr(), cur.data_ptr(), mv.data_ptr(), res.data_ptr(), N, h, w,
+                                             _stream()))
+    return res
 
 
 def to_nhwc(x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:

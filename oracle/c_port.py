@@ -82,3 +82,25 @@ def chain_nq(mv, key, scale_map, cur, logits, im_scale=1.0, tmp=None, out=None):
     load().lsfa_ref_chain_nq(_p(mv), mv.shape[1], mv.shape[2], C.c_double(im_scale), _p(key), _p(scale_map),
                              _p(cur), _p(logits), _p(out), _p(tmp), N, Cc, H, W)
     return out, tmp
+
+
+def mv_accumulate(mvs, counts, height, width):
+    """coviar_data_loader.c:71-139 (accumulate=1) for one GOP: mvs (T,M,6) int32, counts (T,) -> (height,width,2)."""
+    mvs = np.ascontiguousarray(mvs, dtype=np.int32)
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    T, M, _ = mvs.shape
+    a = np.empty(height * width * 2, np.int32)
+    b = np.empty_like(a)
+    out = np.empty((height, width, 2), np.int32)
+    load().lsfa_ref_mv_accumulate(_p(mvs), _p(counts), T, M, height, width, _p(a), _p(b), _p(out))
+    return out
+
+
+def coviar_residual(iframe, cur, mv):
+    iframe = np.ascontiguousarray(iframe, dtype=np.uint8)
+    cur = np.ascontiguousarray(cur, dtype=np.uint8)
+    mv = np.ascontiguousarray(mv, dtype=np.int32)
+    h, w, _ = cur.shape
+    res = np.empty((h, w, 3), np.int32)
+    load().lsfa_ref_coviar_residual(_p(iframe), _p(cur), _p(mv), _p(res), h, w)
+    return res

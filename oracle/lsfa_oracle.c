@@ -195,3 +195,59 @@ EXPORT void lsfa_ref_chain_nq(const int32_t* mv, int mv_h, int mv_w, double im_s
   lsfa_ref_mul(t3, cur, t4, F);
   lsfa_ref_add(t0, t4, out, F);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * coviar's accumulated MV field and residual: a literal restatement of
+ * external/data_loader_py2/coviar_data_loader.c:71-177 (create_and_load_mv_residual with
+ * accumulate = 1) and the identity initialisation of :318-328, minus the FFmpeg / NumPy-C-API
+ * plumbing (those headers are not available offline, so the function cannot be compiled from
+ * the reference file itself).  Kept in the reference's own [x][y][2] layout and loop order.
+ * mvs: (T,M,6) int32 {w,h,src_x,src_y,dst_x,dst_y}, counts (T,), mv_out (height,width,2).
+ * ------------------------------------------------------------------------------------------ */
+EXPORT void lsfa_ref_mv_accumulate(const int32_t* mvs, const int32_t* counts, int T, int M, int height, int width,
+                                   int* accu_src, int* accu_src_old, int32_t* mv_out) {
+  for (int x = 0; x < width; ++x)
+    for (int y = 0; y < height; ++y) {
+      accu_src_old[x * height * 2 + y * 2] = x;
+      accu_src_old[x * height * 2 + y * 2 + 1] = y;
+    }
+  memcpy(accu_src, accu_src_old, (size_t)height * width * 2 * sizeof(int));
+  for (int t = 0; t < T; ++t) {
+    const int n = counts[t] < M ? counts[t] : M;
+    for (int i = 0; i < n; i++) {
+      const int32_t* mv = mvs + ((size_t)t * M + i) * 6;
+      const int w = mv[0], h = mv[1], src_x = mv[2], src_y = mv[3], dst_x = mv[4], dst_y = mv[5];
+      if (dst_x - src_x != 0 || dst_y - src_y != 0) {
+        for (int x_start = (-1 * w / 2); x_start < w / 2; ++x_start) {
+          for (int y_start = (-1 * h / 2); y_start < h / 2; ++y_start) {
+            const int p_dst_x = dst_x + x_start, p_dst_y = dst_y + y_start;
+            const int p_src_x = src_x + x_start, p_src_y = src_y + y_start;
+            if (p_dst_y >= 0 && p_dst_y < height && p_dst_x >= 0 && p_dst_x < width && p_src_y >= 0 &&
+                p_src_y < height && p_src_x >= 0 && p_src_x < width) {
+              for (int c = 0; c < 2; ++c)
+                accu_src[p_dst_x * height * 2 + p_dst_y * 2 + c] = accu_src_old[p_src_x * height * 2 + p_src_y * 2 + c];
+            }
+          }
+        }
+      }
+    }
+    memcpy(accu_src_old, accu_src, (size_t)width * height * 2 * sizeof(int));
+  }
+  for (int x = 0; x < width; ++x)
+    for (int y = 0; y < height; ++y) {
+      mv_out[((size_t)y * width + x) * 2] = x - accu_src[x * height * 2 + y * 2];
+      mv_out[((size_t)y * width + x) * 2 + 1] = y - accu_src[x * height * 2 + y * 2 + 1];
+    }
+}
+
+/* coviar_data_loader.c:141-175, accumulate case: res = cur - iframe[src], src = accu = (x,y) - mv */
+EXPORT void lsfa_ref_coviar_residual(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res,
+                                     int height, int width) {
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      const int src_x = x - mv[((size_t)y * width + x) * 2], src_y = y - mv[((size_t)y * width + x) * 2 + 1];
+      for (int c = 0; c < 3; ++c)
+        res[((size_t)y * width + x) * 3 + c] =
+            (int32_t)cur[((size_t)y * width + x) * 3 + c] - (int32_t)iframe[((size_t)src_y * width + src_x) * 3 + c];
+    }
+}

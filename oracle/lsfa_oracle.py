@@ -66,6 +66,66 @@ def im_scale_for(h, w, target_size=600, max_size=1000):
 
 
 # --------------------------------------------------------------------------------------
+# upstream: coviar's accumulated MV field   coviar_data_loader.c:71-139,318-328
+# --------------------------------------------------------------------------------------
+def coviar_accumulate(mvs, counts, height, width):
+    """Pure-Python literal loop (small cases only): per P-frame, every vector with dst != src, in
+    list order, copies accu_old[src] to accu[dst] for the pixels of its w x h block whose dst
+    AND src are inside the frame; accu starts as the identity; mv = (x,y) - accu."""
+    ident = np.stack(np.meshgrid(np.arange(width), np.arange(height)), -1).astype(np.int32)  # [y,x] = (x,y)
+    old = ident.copy()
+    new = ident.copy()
+    for t in range(mvs.shape[0]):
+        for i in range(min(int(counts[t]), mvs.shape[1])):
+            w, h, sx, sy, dx, dy = (int(v) for v in mvs[t, i])
+            if dx - sx == 0 and dy - sy == 0:
+                continue
+            for xs in range(int(-1 * w / 2), int(w / 2)):          # C division truncates toward zero
+                for ys in range(int(-1 * h / 2), int(h / 2)):
+                    pdx, pdy, psx, psy = dx + xs, dy + ys, sx + xs, sy + ys
+                    if 0 <= pdy < height and 0 <= pdx < width and 0 <= psy < height and 0 <= psx < width:
+                        new[pdy, pdx] = old[psy, psx]
+        old = new.copy()
+    return ident - new
+
+
+def coviar_residual(iframe, cur, mv):
+    """coviar_data_loader.c:141-175 (accumulate case): cur - iframe[(x,y) - mv], int32."""
+    h, w, _ = cur.shape
+    ident = np.stack(np.meshgrid(np.arange(w), np.arange(h)), -1)
+    src = ident - mv
+    return cur.astype(np.int32) - iframe[src[..., 1], src[..., 0]].astype(np.int32)
+
+
+def synth_mv_lists(rng, T, height, width, block=16, max_disp=24, p_move=0.6, extra=4):
+    """Per P-frame motion-vector lists as FFmpeg exports them for MPEG-4: one vector per 16x16
+    macroblock (dst = block centre), a share of them static, plus a few 8x8 vectors that overlap
+    earlier ones and some that point outside the frame.  Returns mvs (T,M,6), counts (T,)."""
+    bx, by = -(-width // block), -(-height // block)
+    M = bx * by + extra
+    mvs = np.zeros((T, M, 6), np.int32)
+    counts = np.zeros(T, np.int32)
+    for t in range(T):
+        k = 0
+        for j in range(by):
+            for i in range(bx):
+                dx, dy = i * block + block // 2, j * block + block // 2
+                if rng.random() < p_move:
+                    ox, oy = (int(v) for v in rng.integers(-max_disp, max_disp + 1, 2))
+                else:
+                    ox = oy = 0
+                mvs[t, k] = (block, block, dx + ox, dy + oy, dx, dy)
+                k += 1
+        for _ in range(extra):
+            dx, dy = int(rng.integers(0, width)), int(rng.integers(0, height))
+            ox, oy = (int(v) for v in rng.integers(-max_disp, max_disp + 1, 2))
+            mvs[t, k] = (8, 8, dx + ox, dy + oy, dx, dy)
+            k += 1
+        counts[t] = k
+    return mvs, counts
+
+
+# --------------------------------------------------------------------------------------
 # a2  stage-1 resize by im_scale                      lib/utils/image.py:204-205
 # --------------------------------------------------------------------------------------
 def _cv_round(v):

@@ -199,6 +199,13 @@ LSFA_API int lsfa_unfused_chain_f32_nchw(const float* key, const float* flow, co
                                 int N, int C, int H, int W, void* stream);
 LSFA_API int lsfa_unfused_chain_num_launches(void);
 
+/* a12/a13 tail on its own (SYM:104-108, 141-147) - K2 of the exact two-phase key-frame graph, where the
+ * warped feature must be materialised for the embedding / Nq convolutions:
+ * out = w1*src0 + w2*cur, (w1,w2) = softmax over logits[n,0|1]; bypass[n] != 0 keeps cur.  NCHW f32. */
+LSFA_API int lsfa_blend_logits_f32(const float* src0, const float* cur, const float* logits,
+                                   const uint8_t* bypass, float* out, int N, int C, int H, int W,
+                                   void* stream);
+
 /* a15 - ChooseFeat (operator_py/choose_feat.py:23-31) with the flag kept on the device:
  * out[n] = eq_flag[n] ? conv_feat[n] : conv_feat_prop[n]; per_frame = C*H*W elements. */
 LSFA_API int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat_prop,

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "lsfa_cosine_logits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "lsfa_unfused_chain_f32_nchw": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lsfa_unfused_chain_num_launches": (_I, []),
+    "lsfa_blend_logits_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lsfa_choose_feat_f32": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P]),
     "lsfa_mv_accumulate_workspace_bytes": (_SZ, [_I, _I, _I]),
     "lsfa_mv_accumulate_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),

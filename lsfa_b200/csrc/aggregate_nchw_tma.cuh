@@ -347,8 +347,9 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
               v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
               v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
               v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
-              sc[g] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;   // slots past the plane read the tail pad
-              cu[g] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
+              const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written
+              sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
+              cu[g] = (has_cur && ok) ? io_s[j * kTmaConsumers] : 0.0f;
             }
           }
 #pragma unroll

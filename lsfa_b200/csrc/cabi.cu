@@ -41,6 +41,8 @@ cudaError_t launch_unfused_chain(const float* key, const float* flow, const floa
 int unfused_chain_launches();
 cudaError_t launch_choose_feat(const float* a, const float* b, const unsigned char* flag, float* o,
                                long long per_frame, long long total, cudaStream_t st);
+cudaError_t launch_blend_logits(const float* src0, const float* cur, const float* logits, const unsigned char* bypass,
+                                float* out, int N, int C, int HW, cudaStream_t st);
 // coviar_accumulate.cu
 cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
                                  int* mv_out, void* workspace, cudaStream_t st);
@@ -364,6 +366,14 @@ int lsfa_choose_feat_f32(const float* conv_feat, const float* conv_feat_prop, co
   return cuda_result(lsfa::launch_choose_feat(conv_feat, conv_feat_prop, eq_flag, out, per_frame,
                                               (long long)N * per_frame, as_stream(stream)),
                      "choose_feat launch");
+}
+
+int lsfa_blend_logits_f32(const float* src0, const float* cur, const float* logits, const uint8_t* bypass, float* out,
+                          int N, int C, int H, int W, void* stream) {
+  if (!src0 || !cur || !logits || !out) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  return cuda_result(lsfa::launch_blend_logits(src0, cur, logits, bypass, out, N, C, H * W, as_stream(stream)),
+                     "blend_logits launch");
 }
 
 size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width) {

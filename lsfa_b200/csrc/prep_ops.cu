@@ -245,6 +245,28 @@ __global__ void choose_feat_kernel(const float* __restrict__ a, const float* __r
   }
 }
 
+// K2 of the exact two-phase key-frame graph: the Nq / Fgfa tail on two materialised features
+// (SYM:104-108, 141-147): out = w1 * src0 + w2 * cur with (w1,w2) = softmax over the two logits,
+// bypass frames keep cur (choose_feat.py:23-31).  Thread = pixel (weights computed once), loop
+// over a slice of channels: every access is coalesced along the pixel axis.  3F of traffic.
+constexpr int kBlendCG = 32;
+__global__ void __launch_bounds__(256)
+blend_logits_kernel(const float* __restrict__ src0, const float* __restrict__ cur, const float* __restrict__ logits,
+                    const unsigned char* __restrict__ bypass, float* __restrict__ out, int C, int HW) {
+  const int n = blockIdx.z;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int c0 = blockIdx.y * kBlendCG, c1 = min(C, c0 + kBlendCG);
+  const bool byp = bypass != nullptr && __ldg(bypass + n) != 0;
+  float ww = 0.f, wc = 1.f;
+  if (!byp) softmax2(__ldg(logits + ((size_t)n * 2) * HW + p), __ldg(logits + ((size_t)n * 2 + 1) * HW + p), ww, wc);
+  size_t e = ((size_t)n * C + c0) * HW + p;
+  for (int c = c0; c < c1; ++c, e += HW) {
+    const float b = ldg_stream(cur + e);
+    out[e] = byp ? b : fmaf(wc, b, ww * ldg_stream(src0 + e));
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -349,6 +371,14 @@ cudaError_t launch_unfused_chain(const float* key, const float* flow, const floa
   return cudaPeekAtLastError();
 }
 int unfused_chain_launches() { return kUnfusedLaunches; }
+
+cudaError_t launch_blend_logits(const float* src0, const float* cur, const float* logits, const unsigned char* bypass,
+                                float* out, int N, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 255) / 256, (C + kBlendCG - 1) / kBlendCG, N);
+  if (grid.y > 65535 || grid.z > 65535) return cudaErrorInvalidValue;
+  blend_logits_kernel<<<grid, 256, 0, st>>>(src0, cur, logits, bypass, out, C, HW);
+  return cudaPeekAtLastError();
+}
 
 cudaError_t launch_choose_feat(const float* a, const float* b, const unsigned char* flag, float* o,
                                long long per_frame, long long total, cudaStream_t st) {

@@ -27,7 +27,7 @@ from . import _cabi as A
 __all__ = [
     "GridGenerator", "BilinearSampler", "mv_prepare", "mv_pool", "res_pool", "transform_mv_res",
     "sampler_coords", "warp_scale_aggregate", "cur_frame_path", "Nq_aggregate", "Fgfa_aggregate",
-    "mean_aggregate", "ChooseFeat", "tile_as", "cosine_logits", "unfused_chain", "mv_accumulate", "coviar_residual", "to_nhwc",
+    "mean_aggregate", "blend_logits", "ChooseFeat", "tile_as", "cosine_logits", "unfused_chain", "mv_accumulate", "coviar_residual", "to_nhwc",
     "to_nchw", "num_launches",
 ]
 
@@ -417,6 +417,22 @@ def ChooseFeat(conv_feat, conv_feat_prop, eq_flag):
     A.check(A.load().lsfa_choose_feat_f32(conv_feat.data_ptr(), conv_feat_prop.data_ptr(),
                                           eq_flag.data_ptr(), out.data_ptr(), n,
                                           conv_feat.numel() // n, _stream()))
+    return out
+
+
+def blend_logits(src0, cur, logits, bypass=None, out=None) -> torch.Tensor:
+    """Nq / Fgfa tail on two materialised features (SYM:104-108,141-147): softmax(logits) blend, NCHW f32."""
+    _dev(src0, "src0", torch.float32)
+    _dev(cur, "cur", torch.float32)
+    _dev(logits, "logits", torch.float32)
+    N, Cc, H, W = src0.shape
+    if cur.shape != src0.shape or tuple(logits.shape) != (N, 2, H, W):
+        raise ValueError("blend_logits: src0/cur (N,C,H,W) and logits (N,2,H,W) expected")
+    if bypass is not None:
+        _dev(bypass, "bypass", torch.uint8)
+    out = torch.empty_like(src0) if out is None else _dev(out, "out", torch.float32)
+    A.check(A.load().lsfa_blend_logits_f32(src0.data_ptr(), cur.data_ptr(), logits.data_ptr(), _ptr(bypass),
+                                           out.data_ptr(), N, Cc, H, W, _stream()))
     return out
 
 

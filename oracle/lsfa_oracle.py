@@ -505,6 +505,57 @@ def batch_path(conv_feat_key, flow, scale_map):
 
 
 # --------------------------------------------------------------------------------------
+# The dense convolutions around the path (library GEMMs in the product; here only so the exact
+# two-phase key-frame graphs can be checked end to end at small sizes)
+# --------------------------------------------------------------------------------------
+def conv2d(x, w, b, pad=0):
+    """mx.sym.Convolution, stride 1: x (N,Ci,H,W), w (Co,Ci,k,k), b (Co,) -> (N,Co,H,W) (float64 accumulate)."""
+    x = np.asarray(x, F64)
+    w = np.asarray(w, F64)
+    k = w.shape[2]
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    N, Ci, Hp, Wp = xp.shape
+    H, W = Hp - k + 1, Wp - k + 1
+    out = np.zeros((N, w.shape[0], H, W), F64)
+    for dy in range(k):
+        for dx in range(k):
+            out += np.einsum("nchw,oc->nohw", xp[:, :, dy:dy + H, dx:dx + W], w[:, :, dy, dx])
+    return (out + np.asarray(b, F64)[None, :, None, None]).astype(F32)
+
+
+def embed_net(x, w1, b1, w2, b2, w3, b3):
+    """get_embednet SYM:118-130."""
+    x = np.maximum(conv2d(x, w1, b1), 0)
+    x = np.maximum(conv2d(x, w2, b2, pad=1), 0)
+    return conv2d(x, w3, b3)
+
+
+def nq_net(x, w1, b1, w2, b2, w3, b3):
+    """Nq_net convs SYM:97-101."""
+    x = np.maximum(conv2d(x, w1, b1, pad=1), 0)
+    x = np.maximum(conv2d(x, w2, b2), 0)
+    return conv2d(x, w3, b3)
+
+
+def key_frame_fgfa_full(feat_key_old, flow, scale_map, conv_feat, embed_params, is_first=None):
+    """get_key_test_symbol, Fgfa branch, convolutions included (SYM:468-470,473-474,132-148,477)."""
+    wp = scale_mul(warp(feat_key_old, flow), scale_map)
+    n = conv_feat.shape[0]
+    emb = embed_net(np.concatenate([conv_feat, wp], 0), *embed_params)
+    out = aggregate_cosine(wp, conv_feat, emb[n:], emb[:n])
+    return choose_feat(np.asarray(conv_feat, F32), out, is_first) if is_first is not None else out
+
+
+def key_frame_nq_full(feat_key_old, flow, scale_map, conv_feat, nq_params, is_first=None):
+    """get_key_test_symbol, Nq branch (shipped), convolutions included (SYM:468-472,94-109,477)."""
+    wp = scale_mul(warp(feat_key_old, flow), scale_map)
+    n = conv_feat.shape[0]
+    q = nq_net(np.concatenate([wp, conv_feat], 0), *nq_params)
+    out = aggregate_logits(wp, conv_feat, q[:n], q[n:])
+    return choose_feat(np.asarray(conv_feat, F32), out, is_first) if is_first is not None else out
+
+
+# --------------------------------------------------------------------------------------
 # Algorithmic bytes (SURVEY.md section 8d) - used by bench.py and DESIGN.md
 # --------------------------------------------------------------------------------------
 def algorithmic_bytes_per_frame(C, H, W, feat_bytes=4, variant="V2", E=2048):

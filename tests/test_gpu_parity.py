@@ -539,3 +539,61 @@ def test_host_aggregator_pipeline(ops, cuda):
     agg.synchronize()
     assert_close_f32(out_host.numpy(), oracle_fused(d, O.W_LOGITS),
                      scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="host pipeline")
+
+
+def test_exact_two_phase_key_frame_graphs(ops, cuda):
+    """get_key_test_symbol end to end (SYM:468-477): K1 warp x scale (lsfa) -> embedding / Nq convolutions
+    (library GEMMs: cuDNN) -> K2 cosine + softmax blend (lsfa), against the oracle with NumPy convolutions."""
+    from lsfa_b200 import graphs
+    rng = np.random.default_rng(4)
+    N, C, H, W = 2, 16, 12, 14
+    d = make_case(4, N, C, H, W)
+    first = np.array([0, 1], np.uint8)
+    mk = lambda *shape: (0.2 * rng.standard_normal(shape)).astype(np.float32)  # noqa: E731
+    emb = (mk(8, C, 1, 1), mk(8), mk(8, 8, 3, 3), mk(8), mk(32, 8, 1, 1), mk(32))
+    nq = (mk(8, C, 3, 3), mk(8), mk(4, 8, 1, 1), mk(4), mk(1, 4, 1, 1), mk(1))
+    t = lambda a: dev(a, cuda)  # noqa: E731
+    # TF32 would break the 1e-5 gate on the convolutions: pin cuDNN to fp32 for this check
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        got_f = graphs.key_frame_fgfa(t(d["key"]), t(d["mv"]), t(d["scale_map"]), t(d["cur"]), [t(a) for a in emb],
+                                      is_first_frame=t(first), flow_kind="raw")
+        got_q = graphs.key_frame_nq(t(d["key"]), t(d["mv"]), t(d["scale_map"]), t(d["cur"]), [t(a) for a in nq],
+                                    is_first_frame=t(first), flow_kind="raw")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    want_f = O.key_frame_fgfa_full(d["key"], d["flow"], d["scale_map"], d["cur"], emb, first)
+    want_q = O.key_frame_nq_full(d["key"], d["flow"], d["scale_map"], d["cur"], nq, first)
+    scale = max(np.abs(d["key"]).max(), np.abs(d["cur"]).max())
+    # the convolutions are library code with their own summation order: 1e-4 relative on the blend weights
+    assert np.abs(host(got_f) - want_f).max() <= 2e-4 * scale
+    assert np.abs(host(got_q) - want_q).max() <= 2e-4 * scale
+    assert np.array_equal(host(got_f)[1], d["cur"][1]) and np.array_equal(host(got_q)[1], d["cur"][1])
+
+
+def test_stream_scheduler_batches_non_key_frames_of_many_streams(ops, cuda):
+    """The batched driver (one key feature per stream, key_index per frame) equals the reference's
+    frame-by-frame loop: every non-key frame of every stream is warped from ITS stream's key feature."""
+    from lsfa_b200.driver import StreamScheduler
+    rng = np.random.default_rng(12)
+    seg_lens = [14, 26, 13]
+    C, H, W = 16, 10, 12
+    sch = StreamScheduler(seg_lens, C, (H, W), cuda)
+    keys = {s: O.synth_features(rng, (1, C, H, W)) for s in sch.stream_ids}
+    for s in sch.stream_ids:
+        sch.set_key_feature(s, dev(keys[s], cuda))
+    rw = (0.01 * rng.standard_normal((C, 3))).astype(np.float32); rb = (0.01 * rng.standard_normal(C)).astype(np.float32)
+    seen = 0
+    for sid, fid, slot in sch.batches(16):
+        B = len(sid)
+        mv = O.synth_raw_mv(rng, B, 16 * H, 16 * W, 32)
+        res = O.res_pool(rng.integers(-64, 65, size=(B, 16 * H, 16 * W, 3), dtype=np.int32))
+        cur = O.synth_features(rng, (B, C, H, W))
+        got = host(sch.run_non_key_batch(slot, dev(mv, cuda), dev(cur, cuda), res=dev(res, cuda), rnet_w=dev(rw, cuda),
+                                         rnet_b=dev(rb, cuda)))
+        for i in range(B):   # the reference's per-frame call (tester.py:251-253 -> SYM:570-586)
+            want = O.cur_frame_path(keys[int(sid[i])], O.mv_pool(mv[i:i + 1]), res[i:i + 1], rw, rb, cur[i:i + 1])
+            assert_close_f32(got[i:i + 1], want, scale=max(np.abs(cur).max(), 5.0), what="stream %d frame %d" % (sid[i], fid[i]))
+        seen += B
+    assert seen == sum(int((sch.flags[s] == 2).sum()) for s in sch.stream_ids)

@@ -130,7 +130,8 @@ typedef struct LsfaAggArgs {
   int32_t mv_hflip;          /* LSFA_FLOW_COVIAR_I32: 1 applies the horizontal flip of image.py:56-60 */
 
   int32_t force_generic;     /* kernel choice (NCHW): 0 auto, 1 generic gather, 2 plane-resident LDG/STG,
-                                3 all-TMA warp-specialised (error if it cannot serve the args) */
+                                3 all-TMA warp-specialised, 4 its experimental 2-CTA-cluster form with a multicast
+                                key load (never chosen automatically); 3 and 4 fail if the kernel cannot serve the args */
 } LsfaAggArgs;
 
 LSFA_API int         lsfa_version(void);

@@ -3,7 +3,7 @@
 // kernel for shapes the fast kernel does not take, and the cosine-logit pre-pass.
 #include <cstdlib>
 
-#include "aggregate_nchw_tma.cuh"
+#include "aggregate_nchw_tma2.cuh"
 
 namespace lsfa {
 
@@ -252,7 +252,8 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   const int part_pix = ppt * kTmaConsumers;
   if ((long long)part_pix * (parts - 1) >= P.HW) return false;   // every part must be non-empty
   const bool has_scale = var == kVarScale || var == kVarScaleCur;
-  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 : 0;
+  // res variant: pooled residual of the frame part [3][part_pix] + the rnet_conv0 table [C] x (w0,w1,w2,b)
+  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 + (size_t)P.C * 16 : 0;
   const int io_plane = parts == 1 ? P.HW : part_pix;             // elements per plane slice in a stage
   const size_t pad = (((size_t)part_pix - (parts == 1 ? P.HW : 0)) * 4 + 127) / 128 * 128;
   const int prefer[2] = {2, 1};
@@ -307,6 +308,74 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
     case kVarScale: return launch_tma_variant<kVarScale>(P, smem, (int)grid, st);
     case kVarScaleCur: return launch_tma_variant<kVarScaleCur>(P, smem, (int)grid, st);
     case kVarResCur: return launch_tma_variant<kVarResCur>(P, smem, (int)grid, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---- 2-CTA cluster kernel (planes that need exactly two pixel parts): planning and dispatch ----
+bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
+  (void)forced;
+  const size_t kSmemMax = 227 * 1024;
+  const int var = variant_of(P);
+  if (var == kVarRuntime) return false;
+  if (P.HWk > 16383 || (P.HW % 4) || (P.HWk % 4)) return false;
+  const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
+  for (const void* q : ptrs)
+    if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
+  const int per_part = (P.HW + 1) / 2;
+  int ppt = 0;
+  if (per_part > 5 * kTmaConsumers && per_part <= 9 * kTmaConsumers) ppt = 9;
+  else if (per_part > 3 * kTmaConsumers && per_part <= 5 * kTmaConsumers) ppt = 5;
+  if (ppt == 0) return false;                                   // one part fits a single CTA, or more than two are needed
+  const int part_pix = ppt * kTmaConsumers;
+  if (part_pix >= P.HW) return false;
+  if (sm_count() < 2) return false;
+  const bool has_scale = var == kVarScale || var == kVarScaleCur;
+  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 + (size_t)P.C * 16 : 0;
+  const int K = 1;
+  const unsigned key_bytes = (unsigned)((size_t)K * P.HWk * 4), io_bytes = (unsigned)((size_t)K * part_pix * 4);
+  const unsigned off_scale = (key_bytes + 127u) / 128u * 128u;
+  const unsigned off_io = has_scale ? off_scale + (io_bytes + 127u) / 128u * 128u : off_scale;
+  const unsigned stage_bytes = off_io + (io_bytes + 127u) / 128u * 128u;
+  long long stages = ((long long)kSmemMax - kTma2HeaderBytes - (long long)res_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 3) return false;
+  P.K = K;
+  P.chunks = P.C / K;
+  P.parts = 2;
+  P.part_pix = part_pix;
+  P.stages = (int)stages;
+  P.stage_bytes = stage_bytes;
+  P.key_bytes = key_bytes;
+  P.io_bytes = io_bytes;
+  P.off_scale = off_scale;
+  P.off_io = off_io;
+  P.items = (long long)P.N * P.chunks;                          // one item = both parts of a (frame, chunk)
+  *smem_out = kTma2HeaderBytes + (size_t)P.stages * stage_bytes + res_bytes;
+  return true;
+}
+
+cudaError_t launch_agg_nchw_tma2(const AggParams& Pin, size_t smem, cudaStream_t st) {
+  AggParams P = Pin;
+  long long clusters = sm_count() / 2;
+  if (clusters > P.items) clusters = P.items;
+  if (P.sched) {
+    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (P.records) {
+    AggParams R = P;
+    R.records = nullptr;
+    cudaError_t e = launch_agg_records(R, const_cast<uint4*>(P.records), st);
+    if (e != cudaSuccess) return e;
+  }
+  P.pdl = 0;
+  const int grid = (int)clusters * 2;
+  switch (variant_of(P)) {
+    case kVarWarpOnly: return launch_tma2_variant<kVarWarpOnly>(P, smem, grid, st);
+    case kVarScale: return launch_tma2_variant<kVarScale>(P, smem, grid, st);
+    case kVarScaleCur: return launch_tma2_variant<kVarScaleCur>(P, smem, grid, st);
+    case kVarResCur: return launch_tma2_variant<kVarResCur>(P, smem, grid, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -38,6 +38,205 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr int kTmaHeaderBytes = 256;   // 16 mbarriers + one item descriptor per stage
 constexpr int kTmaClaim = 4;           // items per dynamic claim (4 x ~1.8 us of work)
 
+// The 15 consumer warps of both all-TMA kernels (single CTA and 2-CTA cluster): shared-memory-only
+// work on the stages the producer warp fills.  fixed_part < 0: the stage descriptor carries a virtual
+// frame (frame * parts + part); fixed_part >= 0 (cluster kernel): it carries the frame, and this CTA
+// always works on pixel part `fixed_part`.
+template <int K, int PPT, int VAR>
+__device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* full, uint64_t* done, volatile int2* desc,
+                                                  unsigned char* ring, float* res_s, float4* rnet_s, const int tid,
+                                                  const int fixed_part) {
+  constexpr bool has_scale = VAR == kVarScale || VAR == kVarScaleCur;
+  constexpr bool has_cur = VAR == kVarScaleCur || VAR == kVarResCur;
+  constexpr bool has_res = VAR == kVarResCur;
+  const bool has_bypass = P.bypass != nullptr;
+  // ================================= consumer warps ==========================================
+  float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
+  unsigned o_top[PPT], o_bot[PPT];
+  unsigned valid = 0;
+  int cur_vf = -1, n = 0;
+  bool byp = false, pdl_synced = false;
+  int s = 0;
+  unsigned ph = 0;
+  const unsigned plane_bytes = (unsigned)P.HWk * 4u;
+  const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
+  (void)ww;
+  constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
+
+  if (has_res) {   // the 1x1 conv's weights (SYM:66) sit in smem: per-item global loads would stall every item
+    for (int c = tid; c < P.C; c += kTmaConsumers)
+      rnet_s[c] = make_float4(__ldg(P.rnet_w + (size_t)c * 3), __ldg(P.rnet_w + (size_t)c * 3 + 1),
+                              __ldg(P.rnet_w + (size_t)c * 3 + 2), __ldg(P.rnet_b + c));
+    asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumers) : "memory");   // consumers only (the producer warp is elsewhere)
+  }
+
+  while (true) {
+    mbar_wait(&full[s], ph);
+    const int vf = desc[s].x;
+    if (vf < 0) break;
+    const int chunk = desc[s].y;
+    if (vf != cur_vf) {  // new frame (or pixel part): rebuild this thread's sampling records
+      cur_vf = vf;
+      int part;
+      if (fixed_part >= 0) {
+        n = vf;
+        part = fixed_part;
+      } else {
+        n = vf / P.parts;
+        part = vf - n * P.parts;
+      }
+      const int pix0 = part * P.part_pix;
+      const int pend = min(P.HW, pix0 + P.part_pix);
+      byp = has_bypass && (__ldg(P.bypass + n) != 0);
+      valid = 0;
+      if (P.records != nullptr) {
+        // records come from the pre-pass (agg_records_kernel): two 16-byte loads per pixel slot
+        if (P.pdl && !pdl_synced) {
+          pdl_wait();                 // first use of the pre-pass's output
+          pdl_synced = true;
+        }
+        uint4 ra[PPT], rb[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const int p = pix0 + tid + j * kTmaConsumers;
+          ra[j] = rb[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (p < pend) {
+            valid |= 1u << j;
+            if (!byp) {
+              const uint4* rp = P.records + 2 * ((size_t)n * P.HW + p);
+              ra[j] = __ldg(rp);
+              rb[j] = __ldg(rp + 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          w00[j] = __uint_as_float(ra[j].x); w01[j] = __uint_as_float(ra[j].y);
+          w10[j] = __uint_as_float(ra[j].z); w11[j] = __uint_as_float(ra[j].w);
+          wc[j] = __uint_as_float(rb[j].x); ww[j] = __uint_as_float(rb[j].y);
+          o_top[j] = rb[j].z; o_bot[j] = rb[j].w;
+          if (has_res) {
+            const int p = pix0 + tid + j * kTmaConsumers;
+            if (p < pend && !byp) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+            }
+          }
+        }
+      } else {
+      // the old records are dead from here on: clearing them first frees their registers for the
+      // load batch below (otherwise ptxas spills the batch and every spill store waits on its load)
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
+        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
+      }
+      // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
+      if (!byp) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (p < pend) prefetch_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+      }
+      // phase A: the loads proper, a few pixel slots at a time (they now hit in L2)
+      constexpr int RG = PPT >= 3 ? 3 : PPT;              // slots per load batch (register budget)
+#pragma unroll
+      for (int j0 = 0; j0 < PPT; j0 += RG) {
+        PixelLoads ld[RG];
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (j < PPT && p < pend && !byp) ld[g] = issue_pixel_loads(P, n, p / P.W, p % P.W);
+        }
+        // phase B: the arithmetic (float64 pooling, exact fp32 grid round trip, softmax, fold)
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const int j = j0 + g;
+          if (j >= PPT) continue;
+          const int p = pix0 + tid + j * kTmaConsumers;
+          if (p < pend) {
+            valid |= 1u << j;
+            if (!byp) {
+              const PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
+              w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
+              wc[j] = t.wc; ww[j] = t.ww;
+              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+              if (has_res) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+              }
+            }
+          }
+        }
+      }
+      }  // in-kernel record build
+    }
+
+    if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
+      unsigned char* stage_s = ring + (size_t)s * P.stage_bytes;
+      const int c0 = chunk * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f, rb = 0.f;
+        if (has_res) {
+          const float4 rw = rnet_s[c0 + k];   // broadcast read
+          rw0 = rw.x; rw1 = rw.y; rw2 = rw.z; rb = rw.w;
+        }
+        const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
+        const float* sc_s = reinterpret_cast<const float*>(stage_s + P.off_scale + (size_t)k * io_plane_bytes) + tid;
+        float* io_s = reinterpret_cast<float*>(stage_s + P.off_io + (size_t)k * io_plane_bytes) + tid;
+#pragma unroll
+        for (int j0 = 0; j0 < PPT; j0 += JG) {
+          float v00[JG], v01[JG], v10[JG], v11[JG], sc[JG], cu[JG];
+#pragma unroll
+          for (int g = 0; g < JG; ++g) {   // all shared-memory reads of the group first ...
+            const int j = j0 + g;
+            if (j < PPT) {
+              v00[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+              v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+              v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+              v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+              const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written
+              sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
+              cu[g] = (has_cur && ok) ? io_s[j * kTmaConsumers] : 0.0f;
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < JG; ++g) {   // ... then the arithmetic and the in-place stores
+            const int j = j0 + g;
+            if (j < PPT) {
+              float v = w00[j] * v00[g];
+              v = fmaf(w01[j], v01[g], v);
+              v = fmaf(w10[j], v10[g], v);
+              v = fmaf(w11[j], v11[g], v);
+              if (has_scale) v *= sc[g];
+              if (has_res) {
+                const int q = tid + j * kTmaConsumers;
+                v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
+                                          res_s[2 * PPT * kTmaConsumers + q]), v);
+              }
+              const float o = has_cur ? fmaf(wc[j], cu[g], v) : v;
+              if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&done[s]);
+    if (++s == P.stages) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+}
+
 template <int K, int PPT, int VAR>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
@@ -51,6 +250,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   volatile int2* desc = reinterpret_cast<volatile int2*>(smem_raw + 128);   // (frame, chunk) of each stage; frame < 0 = stop
   unsigned char* ring = smem_raw + kTmaHeaderBytes;
   float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);  // [3][PPT*480]
+  float4* rnet_s = reinterpret_cast<float4*>(res_s + 3 * PPT * kTmaConsumers);       // [C] (w0,w1,w2,b), res variant only
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -208,179 +408,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
     return;
   }
 
-  // ================================= consumer warps ==========================================
-  float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
-  unsigned o_top[PPT], o_bot[PPT];
-  unsigned valid = 0;
-  int cur_vf = -1, n = 0;
-  bool byp = false, pdl_synced = false;
-  int s = 0;
-  unsigned ph = 0;
-  const unsigned plane_bytes = (unsigned)P.HWk * 4u;
-  const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
-  (void)ww;
-  constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
-
-  while (true) {
-    mbar_wait(&full[s], ph);
-    const int vf = desc[s].x;
-    if (vf < 0) break;
-    const int chunk = desc[s].y;
-    if (vf != cur_vf) {  // new frame (or pixel part): rebuild this thread's sampling records
-      cur_vf = vf;
-      n = vf / P.parts;
-      const int pix0 = (vf - n * P.parts) * P.part_pix;
-      const int pend = min(P.HW, pix0 + P.part_pix);
-      byp = has_bypass && (__ldg(P.bypass + n) != 0);
-      valid = 0;
-      if (P.records != nullptr) {
-        // records come from the pre-pass (agg_records_kernel): two 16-byte loads per pixel slot
-        if (P.pdl && !pdl_synced) {
-          pdl_wait();                 // first use of the pre-pass's output
-          pdl_synced = true;
-        }
-        uint4 ra[PPT], rb[PPT];
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          const int p = pix0 + tid + j * kTmaConsumers;
-          ra[j] = rb[j] = make_uint4(0u, 0u, 0u, 0u);
-          if (p < pend) {
-            valid |= 1u << j;
-            if (!byp) {
-              const uint4* rp = P.records + 2 * ((size_t)n * P.HW + p);
-              ra[j] = __ldg(rp);
-              rb[j] = __ldg(rp + 1);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          w00[j] = __uint_as_float(ra[j].x); w01[j] = __uint_as_float(ra[j].y);
-          w10[j] = __uint_as_float(ra[j].z); w11[j] = __uint_as_float(ra[j].w);
-          wc[j] = __uint_as_float(rb[j].x); ww[j] = __uint_as_float(rb[j].y);
-          o_top[j] = rb[j].z; o_bot[j] = rb[j].w;
-          if (has_res) {
-            const int p = pix0 + tid + j * kTmaConsumers;
-            if (p < pend && !byp) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k)
-                res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
-            }
-          }
-        }
-      } else {
-      // the old records are dead from here on: clearing them first frees their registers for the
-      // load batch below (otherwise ptxas spills the batch and every spill store waits on its load)
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
-        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
-      }
-      // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
-      if (!byp) {
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-          const int p = pix0 + tid + j * kTmaConsumers;
-          if (p < pend) prefetch_pixel_loads(P, n, p / P.W, p % P.W);
-        }
-      }
-      // phase A: the loads proper, a few pixel slots at a time (they now hit in L2)
-      constexpr int RG = PPT >= 3 ? 3 : PPT;              // slots per load batch (register budget)
-#pragma unroll
-      for (int j0 = 0; j0 < PPT; j0 += RG) {
-        PixelLoads ld[RG];
-#pragma unroll
-        for (int g = 0; g < RG; ++g) {
-          const int j = j0 + g;
-          const int p = pix0 + tid + j * kTmaConsumers;
-          if (j < PPT && p < pend && !byp) ld[g] = issue_pixel_loads(P, n, p / P.W, p % P.W);
-        }
-        // phase B: the arithmetic (float64 pooling, exact fp32 grid round trip, softmax, fold)
-#pragma unroll
-        for (int g = 0; g < RG; ++g) {
-          const int j = j0 + g;
-          if (j >= PPT) continue;
-          const int p = pix0 + tid + j * kTmaConsumers;
-          if (p < pend) {
-            valid |= 1u << j;
-            if (!byp) {
-              const PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
-              w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
-              wc[j] = t.wc; ww[j] = t.ww;
-              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
-              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
-              if (has_res) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                  res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
-              }
-            }
-          }
-        }
-      }
-      }  // in-kernel record build
-    }
-
-    if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
-      unsigned char* stage_s = ring + (size_t)s * P.stage_bytes;
-      const int c0 = chunk * K;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f, rb = 0.f;
-        if (has_res) {
-          rw0 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 0);
-          rw1 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 1);
-          rw2 = __ldg(P.rnet_w + (size_t)(c0 + k) * 3 + 2);
-          rb = __ldg(P.rnet_b + c0 + k);
-        }
-        const unsigned char* plane_s = stage_s + (size_t)k * plane_bytes;
-        const float* sc_s = reinterpret_cast<const float*>(stage_s + P.off_scale + (size_t)k * io_plane_bytes) + tid;
-        float* io_s = reinterpret_cast<float*>(stage_s + P.off_io + (size_t)k * io_plane_bytes) + tid;
-#pragma unroll
-        for (int j0 = 0; j0 < PPT; j0 += JG) {
-          float v00[JG], v01[JG], v10[JG], v11[JG], sc[JG], cu[JG];
-#pragma unroll
-          for (int g = 0; g < JG; ++g) {   // all shared-memory reads of the group first ...
-            const int j = j0 + g;
-            if (j < PPT) {
-              v00[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
-              v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
-              v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
-              v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
-              const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written
-              sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
-              cu[g] = (has_cur && ok) ? io_s[j * kTmaConsumers] : 0.0f;
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < JG; ++g) {   // ... then the arithmetic and the in-place stores
-            const int j = j0 + g;
-            if (j < PPT) {
-              float v = w00[j] * v00[g];
-              v = fmaf(w01[j], v01[g], v);
-              v = fmaf(w10[j], v10[g], v);
-              v = fmaf(w11[j], v11[g], v);
-              if (has_scale) v *= sc[g];
-              if (has_res) {
-                const int q = tid + j * kTmaConsumers;
-                v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
-                                          res_s[2 * PPT * kTmaConsumers + q]), v);
-              }
-              const float o = has_cur ? fmaf(wc[j], cu[g], v) : v;
-              if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
-            }
-          }
-        }
-      }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
-    }
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&done[s]);
-    if (++s == P.stages) {
-      s = 0;
-      ph ^= 1u;
-    }
-  }
+  tma_consumer_loop<K, PPT, VAR>(P, full, done, desc, ring, res_s, rnet_s, tid, -1);
 }
 
 template <int VAR>

@@ -12,6 +12,8 @@ namespace lsfa {
 // aggregate_nchw.cu
 bool plan_plane_kernel(AggParams& P, size_t* smem_out);
 bool plan_tma_kernel(AggParams& P, size_t* smem_out);
+bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced);
+cudaError_t launch_agg_nchw_tma2(const AggParams& P, size_t smem, cudaStream_t st);
 cudaError_t launch_agg_nchw_tma(const AggParams& P, size_t smem, cudaStream_t st);
 cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t st);
 cudaError_t launch_agg_nchw_generic(const AggParams& P, cudaStream_t st);
@@ -204,6 +206,12 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
     size_t smem = 0;
     // kernel choice: 0 auto (all-TMA, then plane-resident LDG/STG, then generic); the other
     // values pin one kernel for tests and ablations
+    // The 2-CTA cluster form (multicast key load) is opt-in: measured on 1024x68x120 it reaches 0.65 of the
+    // HBM peak against 0.81 for the single-CTA kernel with two pixel parts - with only 3 stages of 67 KB the
+    // cross-CTA hand-shake per refill (peer_free -> claim -> desc_ready) leaves the pair latency-bound.
+    if (a->force_generic == 4 && lsfa::plan_tma2_kernel(P, &smem, true))
+      return cuda_result(lsfa::launch_agg_nchw_tma2(P, smem, st), "agg_nchw_tma2 launch");
+    if (a->force_generic == 4) return fail(LSFA_E_UNSUPPORTED, "the 2-CTA cluster kernel cannot serve these arguments");
     if ((a->force_generic == 0 || a->force_generic == 3) && lsfa::plan_tma_kernel(P, &smem))
       return cuda_result(lsfa::launch_agg_nchw_tma(P, smem, st), "agg_nchw_tma launch");
     if (a->force_generic == 3) return fail(LSFA_E_UNSUPPORTED, "the all-TMA kernel cannot serve these arguments");

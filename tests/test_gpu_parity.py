@@ -281,6 +281,35 @@ def test_all_tma_kernel_every_variant(ops, cuda, variant, shape):
     assert_close_f32(host(got), want, scale=scale, what="tma %s %s" % (variant, shape))
 
 
+@pytest.mark.parametrize("variant", ["warp", "scale", "scale_cur", "res_cur"])
+@pytest.mark.parametrize("shape", [(3, 8, 68, 120), (5, 6, 60, 60), (2, 4, 40, 100)])
+def test_cluster_multicast_kernel(ops, cuda, variant, shape):
+    """force_generic=4 pins the 2-CTA cluster kernel (multicast key load, one pixel part per CTA); it must give
+    the same bits as the single-CTA all-TMA kernel and pass the oracle gate, bypass frames included."""
+    N, C, H, W = shape
+    d = make_case(70 + N, N, C, H, W, max_px=64, with_res=(variant == "res_cur"),
+                  with_bypass=(variant in ("scale_cur", "res_cur")))
+    args = {"warp": ("none", dict(use_scale=False)), "scale": ("none", {}), "scale_cur": ("logits", {}),
+            "res_cur": ("add", dict(use_scale=False, use_res=True))}[variant]
+    mode = {"none": O.W_NONE, "logits": O.W_LOGITS, "add": O.W_ADD}[args[0]]
+    want = oracle_fused(d, mode, **args[1])
+    got4 = run_fused(ops, cuda, d, args[0], "nchw", force_generic=4, **args[1])
+    got3 = run_fused(ops, cuda, d, args[0], "nchw", force_generic=3, **args[1])
+    assert torch.equal(got4, got3)
+    assert_close_f32(host(got4), want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="cluster %s" % variant)
+    # static split (no scratch) and repeated launches
+    t = lambda k: dev(d[k], cuda)  # noqa: E731
+    if variant == "scale_cur":
+        kw = dict(flow_kind="raw", cur=t("cur"), scale_map=t("scale_map"), weight_mode="logits", logits=t("logits"),
+                  bypass=t("bypass"), force_generic=4)
+        st = ops.warp_scale_aggregate(t("key"), t("mv"), workspace=False, **kw)
+        assert torch.equal(st, got4)
+        prep = ops.PreparedAggregate(t("key"), t("mv"), **kw)
+        for _ in range(5):
+            prep.run()
+        assert torch.equal(prep.out, got4)
+
+
 def test_all_tma_static_and_dynamic_split_agree(ops, cuda):
     """With a workspace the all-TMA kernel claims work dynamically (per-frame queues); without one it
     uses a static contiguous split.  Same bits either way, and repeated launches reuse the scratch."""

@@ -159,8 +159,7 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
           if (has_cur) bulk_g2s(st + P.off_io + dk, static_cast<const float*>(P.cur) + ek, len_bytes, &full[s]);
         }
       };
-      auto issue_store = [&](int s) {
-        const int n = desc[s].x, chunk = desc[s].y;
+      auto issue_store = [&](int s, int n, int chunk) {
         unsigned char* st = ring + (size_t)s * P.stage_bytes;
         float* dst = static_cast<float*>(P.out) + ((size_t)n * P.C + (size_t)chunk * K) * P.HW + pix0;
 #pragma unroll
@@ -168,48 +167,54 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
           bulk_s2g(dst + (size_t)k * P.HW, st + P.off_io + (uint32_t)k * (uint32_t)P.part_pix * 4u, len_bytes);
         bulk_commit();
       };
-      // Fill stage s for its round r.  Returns false when the work is exhausted (stop descriptor sent).
-      auto acquire_and_issue = [&](int s, int r) -> bool {
-        int n = -1, chunk = 0;
+      // Refill of stage s for its round r, in two steps so the key multicast overlaps the drain of the out store:
+      //   begin_refill : hand-shake (the consumers of BOTH CTAs are done with the stage: its key region is free),
+      //                  descriptor exchange, arm full[s], multicast key.        -> false: work exhausted
+      //   finish_refill: after this CTA's store has drained the io region: this CTA's own scale / cur slices.
+      int nn = -1, nchunk = 0;                       // leader: the item claimed ahead of time (hides the atomic)
+      bool have_next = false;
+      if (rank == 0) have_next = next_item(nn, nchunk);
+      int cur_n = -1, cur_chunk = 0;
+      bool cur_byp = false;
+      auto begin_refill = [&](int s, int r) -> bool {
         if (rank == 0) {
-          if (r > 0) mbar_wait_cluster(&peer_free[s], (unsigned)(r - 1) & 1u);   // the peer's stage is reusable too
-          const bool ok = next_item(n, chunk);
-          if (!ok) n = -1;
-          desc[s].x = n;
-          desc[s].y = chunk;
-          remote_store_v2(map_to_cta((const void*)&desc[s], 1), n, chunk);
+          if (r > 0) mbar_wait_cluster(&peer_free[s], (unsigned)(r - 1) & 1u);   // the peer's consumers left the stage
+          cur_n = have_next ? nn : -1;
+          cur_chunk = nchunk;
+          desc[s].x = cur_n;
+          desc[s].y = cur_chunk;
+          remote_store_v2(map_to_cta((const void*)&desc[s], 1), cur_n, cur_chunk);
           remote_arrive(map_to_cta(&desc_ready[s], 1));
-          if (!ok) {
-            mbar_arrive(&full[s]);            // stop sentinel for the local consumers
-            return false;
-          }
         } else {
-          if (r > 0) remote_arrive(map_to_cta(&peer_free[s], 0));                 // my stage s is free: the leader may multicast
           mbar_wait_cluster(&desc_ready[s], (unsigned)r & 1u);
-          n = desc[s].x;
-          chunk = desc[s].y;
-          if (n < 0) {
-            mbar_arrive(&full[s]);
-            return false;
-          }
+          cur_n = desc[s].x;
+          cur_chunk = desc[s].y;
         }
-        const bool byp = has_bypass && __ldg(P.bypass + n) != 0;
+        if (cur_n < 0) {
+          mbar_arrive(&full[s]);                      // stop sentinel for the local consumers
+          return false;
+        }
+        cur_byp = has_bypass && __ldg(P.bypass + cur_n) != 0;
         uint32_t bytes = has_cur ? io_tx : 0u;
-        if (!byp) bytes += P.key_bytes + (has_scale ? io_tx : 0u);
+        if (!cur_byp) bytes += P.key_bytes + (has_scale ? io_tx : 0u);
         mbar_expect_tx(&full[s], bytes);
-        if (rank == 0 && !byp) {
-          const int kn = P.key_index ? __ldg(P.key_index + n) : n;
-          const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
-          bulk_g2s_multicast(ring + (size_t)s * P.stage_bytes, ksrc, P.key_bytes, &full[s], (uint16_t)0x3);
+        if (rank == 0) {
+          if (!cur_byp) {
+            const int kn = P.key_index ? __ldg(P.key_index + cur_n) : cur_n;
+            const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)cur_chunk * K) * P.HWk;
+            bulk_g2s_multicast(ring + (size_t)s * P.stage_bytes, ksrc, P.key_bytes, &full[s], (uint16_t)0x3);
+          }
+          have_next = next_item(nn, nchunk);          // claim the following item while this one is in flight
         }
-        issue_own_loads(s, n, chunk, byp);
         return true;
       };
+      auto finish_refill = [&](int s) { issue_own_loads(s, cur_n, cur_chunk, cur_byp); };
 
       int live = 0;
       bool stopped = false;
       for (int s = 0; s < P.stages; ++s) {
-        if (acquire_and_issue(s, 0)) {
+        if (begin_refill(s, 0)) {
+          finish_refill(s);
           ++live;
         } else {
           stopped = true;
@@ -220,12 +225,18 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
       unsigned ph = 0;
       while (live > 0) {
         mbar_wait(&done[s], ph);                       // own consumers finished this stage; out slice is in smem
-        issue_store(s);
+        const int sn = desc[s].x, schunk = desc[s].y;  // read BEFORE the leader may overwrite this descriptor remotely
+        if (rank == 1 && !stopped) remote_arrive(map_to_cta(&peer_free[s], 0));   // key region free: leader may multicast
+        issue_store(s, sn, schunk);
         --live;
         if (!stopped) {
-          bulk_wait_read_all();                        // my stage is drained (the peer is told inside acquire_and_issue)
-          if (acquire_and_issue(s, round + 1)) ++live;
-          else stopped = true;
+          if (begin_refill(s, round + 1)) {
+            bulk_wait_read_all();                      // the store has drained the io region of this stage
+            finish_refill(s);
+            ++live;
+          } else {
+            stopped = true;
+          }
         }
         if (++s == P.stages) {
           s = 0;

@@ -334,7 +334,7 @@ def run_ours(args):
             t_probe = time.perf_counter()
             fps1, cores, _ = cpu_reference_fps(8, reps=1, warmup=1)
             probe = time.perf_counter() - t_probe
-            reps = int(max(2, min(40, 12.0 / max(8 / fps1, 1e-3))))
+            reps = int(max(2, min(800, 15.0 / max(8 / fps1, 1e-3))))     # ~15 s of CPU work
             fps, cores, _ = cpu_reference_fps(8, reps=reps, warmup=0)
             cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "8 frames x %d repetitions (~%.0f s) of the same workload; C port of the MXNet "

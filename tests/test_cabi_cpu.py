@@ -82,6 +82,11 @@ def test_argument_validation_needs_no_gpu(lib):
     a = A.new_args(N=1, C=8, H=38, W=63, req=A.REQ_WRITE, key=16, flow=16, out=16, flow_kind=A.FLOW_COVIAR_I32,
                    mv_src_h=720, mv_src_w=1280, mv_h=562, mv_w=999, im_scale=0.78125)
     assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_SHAPE             # 1280*0.78125 rounds to 1000, not 999
+    a = A.new_args(N=1, C=4, H=4096, W=4096, req=A.REQ_WRITE, key=16, flow=16, out=16)
+    assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_SHAPE             # planes of 2^24 pixels are refused, not truncated
+    a = A.new_args(N=1, C=4, H=4, W=4, req=A.REQ_NULL, key=16, flow=16, out=16)
+    assert lib.lsfa_warp_scale_aggregate(a, None) == A.OK                  # kNullOp: validated, nothing launched
+    assert lib.lsfa_warp_scale_aggregate_num_launches(a) == 0
     assert lib.lsfa_unfused_chain_num_launches() == 9
 
 

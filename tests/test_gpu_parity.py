@@ -626,3 +626,18 @@ def test_stream_scheduler_batches_non_key_frames_of_many_streams(ops, cuda):
             assert_close_f32(got[i:i + 1], want, scale=max(np.abs(cur).max(), 5.0), what="stream %d frame %d" % (sid[i], fid[i]))
         seen += B
     assert seen == sum(int((sch.flags[s] == 2).sum()) for s in sch.stream_ids)
+
+
+def test_config1_single_frame_full_size(ops, cuda):
+    """BASELINE.json configs[0]: one non-key frame, 1x1024x38x63 fp32 key feature + a 600x1000 MV field,
+    GridGenerator(warp) + BilinearSampler as two drop-in operators."""
+    rng = np.random.default_rng(1)
+    key = O.synth_features(rng, (1, 1024, 38, 63))
+    mv = O.synth_raw_mv(rng, 1, 600, 1000, 96)
+    flow = ops.mv_pool(dev(mv, cuda))
+    assert np.array_equal(host(flow), O.mv_pool(mv))
+    grid = ops.GridGenerator(flow, transform_type="warp")
+    out = ops.BilinearSampler(dev(key, cuda), grid)
+    want_grid = O.grid_generator_warp(O.mv_pool(mv))
+    assert np.array_equal(host(grid).view(np.uint32), want_grid.view(np.uint32))
+    assert_close_f32(host(out), O.bilinear_sampler(key, want_grid), scale=np.abs(key).max(), what="config 1")

@@ -229,6 +229,33 @@ LSFA_API int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, i
 LSFA_API int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res,
                                      int N, int height, int width, void* stream);
 
+/* ---- backward of a7 / a8 (get_train_symbol SYM:305-307,319-321) ---------------
+ * MXNet BilinearSamplerBackward (src/operator/bilinear_sampler.cc) and GridGenerator Backward, kWarp
+ * (src/operator/grid_generator-inl.h).  req_* follow OpReqType; kNullOp (or a NULL pointer) skips that
+ * gradient - MXNet itself insists on both or neither, which is accepted here as a special case.
+ *
+ * a8 backward: data (N,C,Hi,Wi), grid (N,2,Ho,Wo), out_grad (N,C,Ho,Wo) ->
+ *              grad_data (N,C,Hi,Wi), grad_grid (N,2,Ho,Wo); float32 NCHW.
+ * workspace (optional, lsfa_bilinear_sampler_backward_workspace_bytes, 16-byte aligned, no initialisation
+ * needed) enables the plane-resident gather kernel (deterministic grad_data, 3 launches); without it, or
+ * for planes it cannot hold, the scatter kernel with global atomics runs (1 launch).
+ * kernel: 0 auto, 1 scatter, 2 gather (LSFA_E_UNSUPPORTED if it cannot serve the arguments). */
+LSFA_API size_t lsfa_bilinear_sampler_backward_workspace_bytes(int N, int C, int Hi, int Wi, int Ho, int Wo);
+LSFA_API int lsfa_bilinear_sampler_backward_f32(const float* data, const float* grid, const float* out_grad,
+                                                float* grad_data, float* grad_grid, int N, int C, int Hi, int Wi,
+                                                int Ho, int Wo, int req_data, int req_grid, void* workspace,
+                                                size_t workspace_bytes, int kernel, void* stream);
+LSFA_API int lsfa_bilinear_sampler_backward_num_launches(int N, int C, int Hi, int Wi, int Ho, int Wo, int req_data,
+                                                         int req_grid, size_t workspace_bytes, int kernel);
+/* a7 backward: grad_flow = grad_grid / [(W-1)/2, (H-1)/2]; (N,2,H,W) float32. */
+LSFA_API int lsfa_grid_generator_warp_backward_f32(const float* grad_grid, float* grad_flow, int N, int H, int W,
+                                                   int req, void* stream);
+/* a7+a8 backward in one pass: gradients of BilinearSampler(key, GridGenerator(flow, 'warp')) with respect
+ * to key (N,C,H,W) and flow (N,2,H,W) (SYM:306-307: both; SYM:320-321: key only). */
+LSFA_API int lsfa_warp_backward_f32(const float* key, const float* flow, const float* out_grad, float* grad_key,
+                                    float* grad_flow, int N, int C, int H, int W, int req_key, int req_flow,
+                                    void* workspace, size_t workspace_bytes, int kernel, void* stream);
+
 /* layout helpers for the harness: NCHW f32 <-> NHWC {f32,bf16} */
 LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout,
                       void* stream);

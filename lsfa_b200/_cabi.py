@@ -85,6 +85,11 @@ PROTOTYPES = {
     "lsfa_mv_accumulate_workspace_bytes": (_SZ, [_I, _I, _I]),
     "lsfa_mv_accumulate_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "lsfa_coviar_residual_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "lsfa_bilinear_sampler_backward_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "lsfa_bilinear_sampler_backward_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _I, _P]),
+    "lsfa_bilinear_sampler_backward_num_launches": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _SZ, _I]),
+    "lsfa_grid_generator_warp_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "lsfa_warp_backward_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _I, _P]),
     "lsfa_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lsfa_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }

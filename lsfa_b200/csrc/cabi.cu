@@ -50,6 +50,15 @@ cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T
                                  int* mv_out, void* workspace, cudaStream_t st);
 cudaError_t launch_coviar_residual(const unsigned char* iframe, const unsigned char* cur, const int* mv, int* res, int N,
                                    int height, int width, cudaStream_t st);
+// sampler_backward.cu
+size_t bwd_workspace_bytes(int N, int HWk, int HW);
+cudaError_t launch_sampler_backward(const float* data, const float* coords, int coords_is_flow, const float* og,
+                                    float* gdata, float* ggrid, int N, int C, int Hi, int Wi, int Ho, int Wo,
+                                    int add_data, int add_grid, float half_w, float half_h, void* workspace,
+                                    size_t workspace_bytes, int kernel, cudaStream_t st);
+int sampler_backward_num_launches(int N, int C, int Hi, int Wi, int Ho, int Wo, bool want_data, bool ws_ok, int kernel);
+cudaError_t launch_grid_generator_backward(const float* g, float* o, int N, int H, int W, float half_w, float half_h,
+                                           int add, cudaStream_t st);
 }  // namespace lsfa
 
 namespace {
@@ -408,6 +417,68 @@ int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int
   if (reinterpret_cast<uintptr_t>(mv) % 8) return fail(LSFA_E_ALIGN, "mv must be 8-byte aligned");
   return cuda_result(lsfa::launch_coviar_residual(iframe, cur, mv, res, N, height, width, as_stream(stream)),
                      "coviar_residual launch");
+}
+
+static int sampler_backward_common(const float* data, const float* coords, int is_flow, const float* og, float* gdata,
+                                   float* ggrid, int N, int C, int Hi, int Wi, int Ho, int Wo, int req_data,
+                                   int req_grid, void* workspace, size_t workspace_bytes, int kernel, void* stream) {
+  if (!valid_req(req_data) || !valid_req(req_grid)) return fail(LSFA_E_BADARG, "unknown req %d / %d", req_data, req_grid);
+  if (kernel < 0 || kernel > 2) return fail(LSFA_E_BADARG, "kernel must be 0 (auto), 1 (scatter) or 2 (gather)");
+  if (N <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0)
+    return fail(LSFA_E_SHAPE, "non-positive dims N=%d C=%d in %dx%d out %dx%d", N, C, Hi, Wi, Ho, Wo);
+  if ((long long)Hi * Wi >= (1LL << 24) || (long long)Ho * Wo >= (1LL << 24))
+    return fail(LSFA_E_SHAPE, "planes of 2^24 pixels or more are not supported");
+  if (req_data == LSFA_REQ_NULL) gdata = nullptr;
+  if (req_grid == LSFA_REQ_NULL) ggrid = nullptr;
+  if (!gdata && !ggrid) return LSFA_OK;                        // nothing requested
+  if (!data || !coords || !og) return fail(LSFA_E_BADARG, "data, grid/flow and out_grad are required");
+  cudaError_t e = lsfa::launch_sampler_backward(data, coords, is_flow, og, gdata, ggrid, N, C, Hi, Wi, Ho, Wo,
+                                                req_data == LSFA_REQ_ADD, req_grid == LSFA_REQ_ADD, half_extent(Wo),
+                                                half_extent(Ho), workspace, workspace_bytes, kernel, as_stream(stream));
+  if (e == cudaErrorNotSupported) {
+    cudaGetLastError();
+    return fail(LSFA_E_UNSUPPORTED, "the gather kernel cannot serve these arguments (workspace, plane size or alignment)");
+  }
+  return cuda_result(e, "sampler backward launch");
+}
+
+size_t lsfa_bilinear_sampler_backward_workspace_bytes(int N, int C, int Hi, int Wi, int Ho, int Wo) {
+  (void)C;
+  if (N <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  return lsfa::bwd_workspace_bytes(N, Hi * Wi, Ho * Wo);
+}
+
+int lsfa_bilinear_sampler_backward_f32(const float* data, const float* grid, const float* out_grad, float* grad_data,
+                                       float* grad_grid, int N, int C, int Hi, int Wi, int Ho, int Wo, int req_data,
+                                       int req_grid, void* workspace, size_t workspace_bytes, int kernel, void* stream) {
+  return sampler_backward_common(data, grid, 0, out_grad, grad_data, grad_grid, N, C, Hi, Wi, Ho, Wo, req_data, req_grid,
+                                 workspace, workspace_bytes, kernel, stream);
+}
+
+int lsfa_bilinear_sampler_backward_num_launches(int N, int C, int Hi, int Wi, int Ho, int Wo, int req_data, int req_grid,
+                                                size_t workspace_bytes, int kernel) {
+  if (N <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  if (req_data == LSFA_REQ_NULL && req_grid == LSFA_REQ_NULL) return 0;
+  return lsfa::sampler_backward_num_launches(N, C, Hi, Wi, Ho, Wo, req_data != LSFA_REQ_NULL,
+                                             workspace_bytes >= lsfa::bwd_workspace_bytes(N, Hi * Wi, Ho * Wo), kernel);
+}
+
+int lsfa_grid_generator_warp_backward_f32(const float* grad_grid, float* grad_flow, int N, int H, int W, int req,
+                                          void* stream) {
+  if (!valid_req(req)) return fail(LSFA_E_BADARG, "unknown req %d", req);
+  if (N <= 0 || H <= 0 || W <= 0) return fail(LSFA_E_SHAPE, "non-positive dims N=%d H=%d W=%d", N, H, W);
+  if (req == LSFA_REQ_NULL) return LSFA_OK;
+  if (!grad_grid || !grad_flow) return fail(LSFA_E_BADARG, "grad_grid and grad_flow are required");
+  return cuda_result(lsfa::launch_grid_generator_backward(grad_grid, grad_flow, N, H, W, half_extent(W), half_extent(H),
+                                                          req == LSFA_REQ_ADD, as_stream(stream)),
+                     "grid_generator backward launch");
+}
+
+int lsfa_warp_backward_f32(const float* key, const float* flow, const float* out_grad, float* grad_key, float* grad_flow,
+                           int N, int C, int H, int W, int req_key, int req_flow, void* workspace, size_t workspace_bytes,
+                           int kernel, void* stream) {
+  return sampler_backward_common(key, flow, 1, out_grad, grad_key, grad_flow, N, C, H, W, H, W, req_key, req_flow,
+                                 workspace, workspace_bytes, kernel, stream);
 }
 
 int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout, void* stream) {

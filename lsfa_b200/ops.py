@@ -25,7 +25,8 @@ import torch
 from . import _cabi as A
 
 __all__ = [
-    "GridGenerator", "BilinearSampler", "mv_prepare", "mv_pool", "res_pool", "transform_mv_res",
+    "GridGenerator", "BilinearSampler", "BilinearSampler_backward", "GridGenerator_backward", "warp_backward",
+    "mv_prepare", "mv_pool", "res_pool", "transform_mv_res",
     "sampler_coords", "warp_scale_aggregate", "cur_frame_path", "Nq_aggregate", "Fgfa_aggregate",
     "mean_aggregate", "blend_logits", "ChooseFeat", "tile_as", "cosine_logits", "unfused_chain", "mv_accumulate", "coviar_residual", "to_nhwc",
     "to_nchw", "num_launches",
@@ -105,6 +106,87 @@ def BilinearSampler(data: torch.Tensor, grid: torch.Tensor, out=None, req="write
     A.check(A.load().lsfa_bilinear_sampler_f32(data.data_ptr(), grid.data_ptr(), out.data_ptr(), N, Cc,
                                                Hi, Wi, Ho, Wo, _REQ[req], _stream()))
     return out
+
+
+_KERNEL = {"auto": 0, "scatter": 1, "gather": 2, 0: 0, 1: 1, 2: 2}
+
+
+def _sampler_backward(fn_name, data, coords, out_grad, grad_data, grad_coords, req_data, req_coords, workspace, kernel):
+    _dev(data, "data", torch.float32)
+    _dev(coords, "grid/flow", torch.float32)
+    _dev(out_grad, "out_grad", torch.float32)
+    if data.dim() != 4 or coords.dim() != 4 or coords.shape[1] != 2 or coords.shape[0] != data.shape[0]:
+        raise ValueError("backward: data (N,C,Hi,Wi) and grid/flow (N,2,Ho,Wo) expected, got %s %s"
+                         % (tuple(data.shape), tuple(coords.shape)))
+    N, Cc, Hi, Wi = data.shape
+    Ho, Wo = coords.shape[2], coords.shape[3]
+    if tuple(out_grad.shape) != (N, Cc, Ho, Wo):
+        raise ValueError("out_grad has shape %s, expected %s" % (tuple(out_grad.shape), (N, Cc, Ho, Wo)))
+    rd, rc = _REQ[req_data], _REQ[req_coords]
+    if rd != A.REQ_NULL:
+        if grad_data is None:
+            if rd == A.REQ_ADD:
+                raise ValueError("req_data='add' needs an existing grad_data")
+            grad_data = torch.empty_like(data)
+        _dev(grad_data, "grad_data", torch.float32)
+        if grad_data.shape != data.shape:
+            raise ValueError("grad_data must have data's shape")
+    if rc != A.REQ_NULL:
+        if grad_coords is None:
+            if rc == A.REQ_ADD:
+                raise ValueError("req_grid='add' needs an existing grad_grid")
+            grad_coords = torch.empty_like(coords)
+        _dev(grad_coords, "grad_grid", torch.float32)
+        if grad_coords.shape != coords.shape:
+            raise ValueError("grad_grid must have the grid's shape")
+    lib = A.load()
+    k = _KERNEL[kernel]
+    if workspace is None and k != 1:
+        need = lib.lsfa_bilinear_sampler_backward_workspace_bytes(N, Cc, Hi, Wi, Ho, Wo)
+        workspace = torch.empty(need, dtype=torch.uint8, device=data.device)
+    ws_ptr, ws_bytes = (None, 0) if workspace is None or workspace is False else (
+        workspace.data_ptr(), workspace.numel() * workspace.element_size())
+    gd = _ptr(grad_data) if rd != A.REQ_NULL else None
+    gc = _ptr(grad_coords) if rc != A.REQ_NULL else None
+    if fn_name == "sampler":
+        A.check(lib.lsfa_bilinear_sampler_backward_f32(data.data_ptr(), coords.data_ptr(), out_grad.data_ptr(), gd, gc,
+                                                       N, Cc, Hi, Wi, Ho, Wo, rd, rc, ws_ptr, ws_bytes, k, _stream()))
+    else:
+        if (Hi, Wi) != (Ho, Wo):
+            raise ValueError("warp_backward: key and flow must share H,W")
+        A.check(lib.lsfa_warp_backward_f32(data.data_ptr(), coords.data_ptr(), out_grad.data_ptr(), gd, gc, N, Cc, Ho, Wo,
+                                           rd, rc, ws_ptr, ws_bytes, k, _stream()))
+    return (grad_data if rd != A.REQ_NULL else None), (grad_coords if rc != A.REQ_NULL else None)
+
+
+def BilinearSampler_backward(data, grid, out_grad, grad_data=None, grad_grid=None, req_data="write", req_grid="write",
+                             workspace=None, kernel="auto"):
+    """Backward of mx.sym.BilinearSampler (MXNet BilinearSamplerBackward): returns (grad_data, grad_grid);
+    a 'null' req skips that gradient (SYM:320-321 needs grad_data only: the motion vector is data)."""
+    return _sampler_backward("sampler", data, grid, out_grad, grad_data, grad_grid, req_data, req_grid, workspace, kernel)
+
+
+def GridGenerator_backward(grad_grid, grad_flow=None, req="write"):
+    """Backward of mx.sym.GridGenerator(transform_type='warp'): grad_flow = grad_grid / [(W-1)/2, (H-1)/2]."""
+    _dev(grad_grid, "grad_grid", torch.float32)
+    if grad_grid.dim() != 4 or grad_grid.shape[1] != 2:
+        raise ValueError("grad_grid must be (N,2,H,W)")
+    rq = _REQ[req]
+    if grad_flow is None:
+        if rq == A.REQ_ADD:
+            raise ValueError("req='add' needs an existing grad_flow")
+        grad_flow = torch.empty_like(grad_grid)
+    _dev(grad_flow, "grad_flow", torch.float32)
+    N, _, H, W = grad_grid.shape
+    A.check(A.load().lsfa_grid_generator_warp_backward_f32(grad_grid.data_ptr(), grad_flow.data_ptr(), N, H, W, rq, _stream()))
+    return grad_flow
+
+
+def warp_backward(key, flow, out_grad, grad_key=None, grad_flow=None, req_key="write", req_flow="write",
+                  workspace=None, kernel="auto"):
+    """Backward of BilinearSampler(key, GridGenerator(flow,'warp')) in one pass (SYM:306-307, 320-321):
+    returns (grad_key, grad_flow)."""
+    return _sampler_backward("warp", key, flow, out_grad, grad_key, grad_flow, req_key, req_flow, workspace, kernel)
 
 
 def sampler_coords(flow_or_grid: torch.Tensor, key_hw=None, is_grid=False):

@@ -49,6 +49,44 @@ def _(data, grid):
     return data.new_empty((data.shape[0], data.shape[1], grid.shape[2], grid.shape[3]))
 
 
+@torch.library.custom_op("lsfa::bilinear_sampler_backward", mutates_args=())
+def bilinear_sampler_backward(data: torch.Tensor, grid: torch.Tensor, out_grad: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    gd, gg = ops.BilinearSampler_backward(data, grid, out_grad.contiguous())
+    return gd, gg
+
+
+@bilinear_sampler_backward.register_fake
+def _(data, grid, out_grad):
+    return torch.empty_like(data), torch.empty_like(grid)
+
+
+@torch.library.custom_op("lsfa::grid_generator_warp_backward", mutates_args=())
+def grid_generator_warp_backward(grad_grid: torch.Tensor) -> torch.Tensor:
+    return ops.GridGenerator_backward(grad_grid.contiguous())
+
+
+@grid_generator_warp_backward.register_fake
+def _(grad_grid):
+    return torch.empty_like(grad_grid)
+
+
+# declare_backward_dependency / backward of the two MXNet operators (operator_py/*.py:declare_backward_dependency
+# is where a CustomOpProp says what its backward needs): the sampler's backward needs data and grid, the grid
+# generator's only the incoming gradient
+def _bs_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _bs_backward(ctx, grad_out):
+    data, grid = ctx.saved_tensors
+    gd, gg = bilinear_sampler_backward(data, grid, grad_out)
+    return gd, gg
+
+
+bilinear_sampler.register_autograd(_bs_backward, setup_context=_bs_setup)
+grid_generator_warp.register_autograd(lambda ctx, g: grid_generator_warp_backward(g))
+
+
 @torch.library.custom_op("lsfa::mv_pool", mutates_args=())
 def mv_pool(mv: torch.Tensor, im_scale: float, mode: int) -> torch.Tensor:
     return ops.mv_pool(mv, im_scale, mode)

@@ -104,3 +104,25 @@ def coviar_residual(iframe, cur, mv):
     res = np.empty((h, w, 3), np.int32)
     load().lsfa_ref_coviar_residual(_p(iframe), _p(cur), _p(mv), _p(res), h, w)
     return res
+
+
+def bilinear_sampler_backward(data, grid, out_grad, grad_data=None, grad_grid=None):
+    """MXNet's CPU BilinearSamplerBackward (sequential float32 accumulation).  grad_data / grad_grid
+    given = kAddTo (accumulated into, in place); None = kWriteTo (zeroed first)."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    grid = np.ascontiguousarray(grid, dtype=np.float32)
+    og = np.ascontiguousarray(out_grad, dtype=np.float32)
+    N, Cc, Hi, Wi = data.shape
+    Ho, Wo = grid.shape[2:]
+    gd = np.zeros_like(data) if grad_data is None else grad_data
+    gg = np.zeros_like(grid) if grad_grid is None else grad_grid
+    load().lsfa_ref_bilinear_sampler_backward(_p(data), _p(grid), _p(og), _p(gd), _p(gg), N, Cc, Hi, Wi, Ho, Wo)
+    return gd, gg
+
+
+def grid_generator_warp_backward(grad_grid):
+    g = np.ascontiguousarray(grad_grid, dtype=np.float32)
+    N, _, H, W = g.shape
+    out = np.empty_like(g)
+    load().lsfa_ref_grid_generator_warp_backward(_p(g), _p(out), N, H, W)
+    return out

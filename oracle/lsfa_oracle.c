@@ -251,3 +251,79 @@ EXPORT void lsfa_ref_coviar_residual(const uint8_t* iframe, const uint8_t* cur, 
             (int32_t)cur[((size_t)y * width + x) * 3 + c] - (int32_t)iframe[((size_t)src_y * width + src_x) * 3 + c];
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the two operators (get_train_symbol, SYM:305-307,319-321).
+ * MXNet src/operator/bilinear_sampler.cc BilinearSamplerBackward, DType = float, restated in
+ * its loop order (n, h, w, c), its sequential float32 `+=` and its float/double promotions
+ * (the `1.0` literals).  g_input and grad_grid are accumulated into: the operator zeroes them
+ * first for kWriteTo (bilinear_sampler-inl.h Backward), which the caller does here.
+ * Single-threaded like the original: the scatter `+=` is order-dependent.
+ * ------------------------------------------------------------------------------------------ */
+EXPORT void lsfa_ref_bilinear_sampler_backward(const float* data, const float* grid, const float* grad,
+                                               float* g_input, float* grad_grid, int o_n, int o_c, int i_h,
+                                               int i_w, int o_h, int o_w) {
+  const int i_c = o_c;
+  for (int n = 0; n < o_n; ++n) {
+    for (int h = 0; h < o_h; ++h) {
+      for (int w = 0; w < o_w; ++w) {
+        float top_left_y_gw = 0.0;
+        float top_left_x_gw = 0.0;
+        const size_t grid_index = (size_t)n * o_h * o_w * 2 + (size_t)h * o_w + w;
+        float y_real = (*(grid + grid_index + (size_t)o_h * o_w) + 1) * (i_h - 1) / 2;
+        float x_real = (*(grid + grid_index) + 1) * (i_w - 1) / 2;
+        float fy = floorf(y_real), fx = floorf(x_real);
+        if (!(fy >= -16777216.0f)) fy = -16777216.0f;
+        if (fy > 16777216.0f) fy = 16777216.0f;
+        if (!(fx >= -16777216.0f)) fx = -16777216.0f;
+        if (fx > 16777216.0f) fx = 16777216.0f;
+        int top_left_y = (int)fy;
+        int top_left_x = (int)fx;
+        float top_left_y_w = 1.0 - (y_real - top_left_y);
+        float top_left_x_w = 1.0 - (x_real - top_left_x);
+        for (int c = 0; c < o_c; ++c) {
+          const size_t grad_index = (((size_t)n * o_c + c) * o_h + h) * o_w + w;
+          const float* plane = data + ((size_t)n * i_c + c) * i_h * i_w;
+          float* gplane = g_input + ((size_t)n * i_c + c) * i_h * i_w;
+          const long data_index = (long)top_left_y * i_w + top_left_x;
+          float top_left_v = 0, top_right_v = 0, bottom_left_v = 0, bottom_right_v = 0;
+          if (between(top_left_x, 0, i_w - 1) && between(top_left_y, 0, i_h - 1)) {
+            *(gplane + data_index) += *(grad + grad_index) * top_left_y_w * top_left_x_w;
+            top_left_v = *(plane + data_index);
+          }
+          if (between(top_left_x + 1, 0, i_w - 1) && between(top_left_y, 0, i_h - 1)) {
+            *(gplane + data_index + 1) += *(grad + grad_index) * top_left_y_w * (1.0 - top_left_x_w);
+            top_right_v = *(plane + data_index + 1);
+          }
+          if (between(top_left_x, 0, i_w - 1) && between(top_left_y + 1, 0, i_h - 1)) {
+            *(gplane + data_index + i_w) += *(grad + grad_index) * (1.0 - top_left_y_w) * top_left_x_w;
+            bottom_left_v = *(plane + data_index + i_w);
+          }
+          if (between(top_left_x + 1, 0, i_w - 1) && between(top_left_y + 1, 0, i_h - 1)) {
+            *(gplane + data_index + i_w + 1) += *(grad + grad_index) * (1.0 - top_left_y_w) * (1.0 - top_left_x_w);
+            bottom_right_v = *(plane + data_index + i_w + 1);
+          }
+          /* grad of the top-left weights; times -1 it is the grad of grid_src */
+          top_left_y_gw -= *(grad + grad_index) * (top_right_v - bottom_right_v +
+                           (top_left_v - top_right_v - bottom_left_v + bottom_right_v) * top_left_x_w);
+          top_left_x_gw -= *(grad + grad_index) * (bottom_left_v - bottom_right_v +
+                           (top_left_v - top_right_v - bottom_left_v + bottom_right_v) * top_left_y_w);
+        }
+        *(grad_grid + grid_index + (size_t)o_h * o_w) += top_left_y_gw * (i_h - 1) / 2;
+        *(grad_grid + grid_index) += top_left_x_gw * (i_w - 1) / 2;
+      }
+    }
+  }
+}
+
+/* GridGenerator backward, kWarp branch (grid_generator-inl.h): gdata = grad / ((dim-1)/2) */
+EXPORT void lsfa_ref_grid_generator_warp_backward(const float* grad, float* gdata, int N, int H, int W) {
+  const float half_w = (float)(((double)(float)W - 1.0) / 2.0);
+  const float half_h = (float)(((double)(float)H - 1.0) / 2.0);
+  for (int n = 0; n < N; ++n)
+    for (int i = 0; i < H * W; ++i) {
+      const size_t o = (size_t)n * 2 * H * W;
+      gdata[o + i] = grad[o + i] / half_w;
+      gdata[o + (size_t)H * W + i] = grad[o + (size_t)H * W + i] / half_h;
+    }
+}

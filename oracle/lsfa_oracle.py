@@ -362,6 +362,71 @@ def warp(key, flow):
 
 
 # --------------------------------------------------------------------------------------
+# backward of a7 / a8 (needed by get_train_symbol SYM:305-307,319-321)
+#     MXNet src/operator/bilinear_sampler.cc BilinearSamplerBackward, grid_generator-inl.h Backward
+#     (kWarp branch).  Not vendored in the reference tree: parity unpinned, like the forward rows;
+#     cross-checked against torch autograd of grid_sample(align_corners=True) in the tests.
+# --------------------------------------------------------------------------------------
+def bilinear_sampler_backward(data, grid, out_grad):
+    """Returns (grad_data, grad_grid) for req = kWriteTo.
+
+    Per output pixel p with top-left index (x0,y0) and top-left weights (wx,wy):
+      grad_data[c, tap] += og[c,p] * {wy*wx, wy*(1-wx), (1-wy)*wx, (1-wy)*(1-wx)}   (taps inside the plane only)
+      gy -= og[c,p] * (v01 - v11 + (v00 - v01 - v10 + v11) * wx)
+      gx -= og[c,p] * (v10 - v11 + (v00 - v01 - v10 + v11) * wy)      (v = 0 outside the plane)
+      grad_grid[1,p] = gy * (Hi-1)/2 ; grad_grid[0,p] = gx * (Wi-1)/2
+    Sums are taken in float64 here (MXNet accumulates sequentially in float32; the C port
+    ``lsfa_ref_bilinear_sampler_backward`` keeps that order) - the GPU gate is a tolerance."""
+    data = np.asarray(data, dtype=F32)
+    og = np.asarray(out_grad, dtype=F32)
+    N, C, Hi, Wi = data.shape
+    _, _, Ho, Wo = og.shape
+    x0, y0, wx, wy = sampler_coords(grid, Hi, Wi)
+    gdata = np.zeros((N, C, Hi * Wi), dtype=F64)
+    ggrid = np.zeros((N, 2, Ho, Wo), dtype=F64)
+    for n in range(N):
+        wxd, wyd = wx[n].astype(F64).ravel(), wy[n].astype(F64).ravel()
+        ogn = og[n].reshape(C, -1).astype(F64)
+        vals = []
+        for dy, dx, w in ((0, 0, wyd * wxd), (0, 1, wyd * (1.0 - wxd)), (1, 0, (1.0 - wyd) * wxd),
+                          (1, 1, (1.0 - wyd) * (1.0 - wxd))):
+            yy, xx = (y0[n] + dy).ravel(), (x0[n] + dx).ravel()
+            ok = (xx >= 0) & (xx <= Wi - 1) & (yy >= 0) & (yy <= Hi - 1)
+            q = np.clip(yy, 0, Hi - 1).astype(np.int64) * Wi + np.clip(xx, 0, Wi - 1)
+            idx = np.nonzero(ok)[0]
+            for c in range(C):
+                np.add.at(gdata[n, c], q[idx], ogn[c, idx] * w[idx])
+            v = np.where(ok[None], data[n].reshape(C, -1)[:, q], F32(0)).astype(F64)
+            vals.append(v)
+        v00, v01, v10, v11 = vals
+        t = v00 - v01 - v10 + v11
+        gy = -np.sum(ogn * (v01 - v11 + t * wxd[None]), axis=0)
+        gx = -np.sum(ogn * (v10 - v11 + t * wyd[None]), axis=0)
+        ggrid[n, 1] = (gy * (Hi - 1) / 2).reshape(Ho, Wo)
+        ggrid[n, 0] = (gx * (Wi - 1) / 2).reshape(Ho, Wo)
+    return gdata.reshape(N, C, Hi, Wi).astype(F32), ggrid.astype(F32)
+
+
+def grid_generator_warp_backward(grad_grid):
+    """gdata = grad / [(W-1)/2, (H-1)/2] broadcast over (N,2,H,W), float32."""
+    g = np.asarray(grad_grid, dtype=F32)
+    N, two, H, W = g.shape
+    half_w = F32((F64(F32(W)) - 1.0) / 2.0)
+    half_h = F32((F64(F32(H)) - 1.0) / 2.0)
+    out = np.empty_like(g)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out[:, 0] = g[:, 0] / half_w
+        out[:, 1] = g[:, 1] / half_h
+    return out
+
+
+def warp_backward(key, flow, out_grad):
+    """Backward of SYM:306-307 / 571-572: (grad_key, grad_flow)."""
+    gk, gg = bilinear_sampler_backward(key, grid_generator_warp(flow), out_grad)
+    return gk, grid_generator_warp_backward(gg)
+
+
+# --------------------------------------------------------------------------------------
 # a9  scale multiply (SYM:308,470,680); a10 res_diff_ada + add (SYM:57-67,575-576)
 # --------------------------------------------------------------------------------------
 def scale_mul(warp_feat, scale_map):

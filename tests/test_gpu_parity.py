@@ -641,3 +641,128 @@ def test_config1_single_frame_full_size(ops, cuda):
     want_grid = O.grid_generator_warp(O.mv_pool(mv))
     assert np.array_equal(host(grid).view(np.uint32), want_grid.view(np.uint32))
     assert_close_f32(host(out), O.bilinear_sampler(key, want_grid), scale=np.abs(key).max(), what="config 1")
+
+
+# ------------------------------------------------------------------------------------------
+# backward of a7 / a8
+# ------------------------------------------------------------------------------------------
+def _bwd_case(seed, N, C, Hi, Wi, Ho, Wo, spread=1.15):
+    rng = np.random.default_rng(seed)
+    data = rng.standard_normal((N, C, Hi, Wi), dtype=np.float32)
+    grid = ((rng.random((N, 2, Ho, Wo), dtype=np.float32) * 2 - 1) * np.float32(spread)).astype(np.float32)
+    og = rng.standard_normal((N, C, Ho, Wo), dtype=np.float32)
+    return data, grid, og
+
+
+@pytest.mark.parametrize("kernel", ["scatter", "gather"])
+@pytest.mark.parametrize("shape", [(2, 8, 38, 63, 38, 63), (3, 6, 12, 20, 9, 14), (1, 4, 20, 24, 30, 36), (2, 3, 7, 8, 5, 8),
+                                   (1, 2, 60, 72, 60, 72)])
+def test_bilinear_sampler_backward(ops, cuda, kernel, shape):
+    N, C, Hi, Wi, Ho, Wo = shape
+    data, grid, og = _bwd_case(sum(shape), *shape)
+    want_d, want_g = O.bilinear_sampler_backward(data, grid, og)
+    if kernel == "gather" and ((C % 2 or (Hi * Wi) % 2 or (Ho * Wo) % 2) and ((Hi * Wi) % 4 or (Ho * Wo) % 4)):
+        with pytest.raises(Exception):
+            ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), kernel=kernel)
+        return
+    gd, gg = ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), kernel=kernel)
+    assert_close_f32(host(gd), want_d, scale=np.abs(want_d).max(), what="grad_data " + kernel)
+    assert_close_f32(host(gg), want_g, scale=np.abs(want_g).max(), what="grad_grid " + kernel)
+    # one gradient at a time (SYM:320-321 needs grad_data only), and kAddTo on both
+    gd1, none = ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), req_grid="null", kernel=kernel)
+    assert none is None
+    assert_close_f32(host(gd1), want_d, scale=np.abs(want_d).max(), what="grad_data only")
+    none, gg1 = ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), req_data="null", kernel=kernel)
+    assert none is None
+    assert_close_f32(host(gg1), want_g, scale=np.abs(want_g).max(), what="grad_grid only")
+    base_d = np.full_like(want_d, 0.5)
+    base_g = np.full_like(want_g, -0.25)
+    gd2, gg2 = ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), grad_data=dev(base_d, cuda),
+                                            grad_grid=dev(base_g, cuda), req_data="add", req_grid="add", kernel=kernel)
+    assert_close_f32(host(gd2), want_d + base_d, scale=np.abs(want_d).max(), what="grad_data kAddTo")
+    assert_close_f32(host(gg2), want_g + base_g, scale=np.abs(want_g).max(), what="grad_grid kAddTo")
+
+
+def test_gather_backward_is_deterministic_and_matches_scatter(ops, cuda):
+    """Lists that fit their slots (here: a sub-cell flow per frame, 4 entries per input pixel) are summed in a
+    fixed order: bit-identical from run to run, unlike the atomic scatter."""
+    data, _, og = _bwd_case(5, 4, 16, 38, 63, 38, 63)
+    flow = np.zeros((4, 2, 38, 63), np.float32)
+    for n, (fx, fy) in enumerate(((0.37, -0.21), (-1.6, 0.4), (2.25, 3.5), (0.0, 0.0))):
+        flow[n, 0], flow[n, 1] = fx, fy
+    a, fa = ops.warp_backward(dev(data, cuda), dev(flow, cuda), dev(og, cuda), kernel="gather")
+    b, fb = ops.warp_backward(dev(data, cuda), dev(flow, cuda), dev(og, cuda), kernel="gather")
+    assert np.array_equal(host(a).view(np.uint32), host(b).view(np.uint32))
+    c, fc = ops.warp_backward(dev(data, cuda), dev(flow, cuda), dev(og, cuda), kernel="scatter")
+    assert_close_f32(host(a), host(c), scale=np.abs(host(c)).max(), what="gather vs scatter")
+    assert_close_f32(host(fa), host(fc), scale=np.abs(host(fc)).max(), what="gather vs scatter grad_flow")
+    want_k, want_f = O.warp_backward(data, flow, og)
+    assert_close_f32(host(a), want_k, scale=np.abs(want_k).max(), what="gather vs oracle")
+
+
+def test_gather_backward_overflowing_lists(ops, cuda):
+    """Every output pixel samples the same spot: one input pixel's list has H*W entries (far beyond the
+    L slots); the overflow fix-up must deliver all of them."""
+    rng = np.random.default_rng(6)
+    N, C, H, W = 2, 4, 38, 63
+    data = rng.standard_normal((N, C, H, W), dtype=np.float32)
+    og = rng.standard_normal((N, C, H, W), dtype=np.float32)
+    grid = np.zeros((N, 2, H, W), np.float32)
+    grid[:, 0] = 0.013
+    grid[:, 1] = -0.2
+    want_d, want_g = O.bilinear_sampler_backward(data, grid, og)
+    gd, gg = ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), kernel="gather")
+    # ~2400 terms per sum: the gate scales with the number of addends
+    assert np.abs(host(gd) - want_d).max() <= 2e-5 * np.abs(want_d).max()
+    assert_close_f32(host(gg), want_g, scale=np.abs(want_g).max(), what="grad_grid")
+
+
+def test_warp_backward_and_grid_generator_backward(ops, cuda):
+    d = make_case(21, 3, 8, 38, 63, max_px=96)
+    rng = np.random.default_rng(22)
+    og = rng.standard_normal(d["cur"].shape, dtype=np.float32)
+    flow = d["flow"].copy()
+    flow[0, :, 0, :4] = [[1000.0, -1000.0, 0.5, -0.5]] * 2          # out of the plane / half-cell flows
+    want_k, want_f = O.warp_backward(d["key"], flow, og)
+    for kernel in ("gather", "scatter"):
+        gk, gf = ops.warp_backward(dev(d["key"], cuda), dev(flow, cuda), dev(og, cuda), kernel=kernel)
+        assert_close_f32(host(gk), want_k, scale=np.abs(want_k).max(), what="grad_key " + kernel)
+        assert_close_f32(host(gf), want_f, scale=np.abs(want_f).max(), what="grad_flow " + kernel)
+    # the same through the two drop-in operators
+    grid = ops.GridGenerator(dev(flow, cuda))
+    gk2, gg = ops.BilinearSampler_backward(dev(d["key"], cuda), grid, dev(og, cuda))
+    gf2 = ops.GridGenerator_backward(gg)
+    assert_close_f32(host(gk2), want_k, scale=np.abs(want_k).max(), what="two-op grad_key")
+    assert_close_f32(host(gf2), want_f, scale=np.abs(want_f).max(), what="two-op grad_flow")
+    g = rng.standard_normal((2, 2, 38, 63), dtype=np.float32)
+    assert np.array_equal(host(ops.GridGenerator_backward(dev(g, cuda))), O.grid_generator_warp_backward(g))
+
+
+def test_backward_full_size_adjoint_property(ops, cuda):
+    """BASELINE size (1024x38x63): <og, forward(data)> == <grad_data, data> - the backward is the exact
+    transpose of the forward operator, checked without an oracle pass over the full tensors."""
+    rng = np.random.default_rng(8)
+    N, C, H, W = 4, 1024, 38, 63
+    data = torch.from_numpy(rng.standard_normal((N, C, H, W), dtype=np.float32)).to(cuda)
+    og = torch.from_numpy(rng.standard_normal((N, C, H, W), dtype=np.float32)).to(cuda)
+    mv = O.synth_raw_mv(rng, N, 600, 1000, 96)
+    flow = ops.mv_pool(dev(mv, cuda))
+    out = ops.warp_scale_aggregate(data, flow)
+    gk, gf = ops.warp_backward(data, flow, og)
+    lhs = float((og.double() * out.double()).sum())
+    rhs = float((gk.double() * data.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * (og.double().abs() * out.double().abs()).sum().item()
+    assert torch.isfinite(gf).all()
+
+
+def test_torch_autograd_through_the_custom_ops(ops, cuda):
+    from lsfa_b200 import torch_ops as T
+    data, grid, og = _bwd_case(9, 2, 4, 38, 63, 38, 63)
+    flow = (np.random.default_rng(10).standard_normal((2, 2, 38, 63)) * 2).astype(np.float32)
+    td = dev(data, cuda).requires_grad_(True)
+    tf = dev(flow, cuda).requires_grad_(True)
+    out = T.bilinear_sampler(td, T.grid_generator_warp(tf))
+    out.backward(dev(og, cuda))
+    want_k, want_f = O.warp_backward(data, flow, og)
+    assert_close_f32(host(td.grad), want_k, scale=np.abs(want_k).max(), what="autograd grad_data")
+    assert_close_f32(host(tf.grad), want_f, scale=np.abs(want_f).max(), what="autograd grad_flow")

@@ -64,12 +64,40 @@ def row(name, frames, alg_bytes_per_frame, ms, pk, note=""):
     return r
 
 
+def backward_rows(dev, pk, quick):
+    """Backward of GridGenerator(warp)+BilinearSampler (8f rank 4) at the headline shape.  Algorithmic bytes per
+    frame: out_grad + grad_key (+ key when d/d(flow) is wanted) = 2F / 3F, + 8*HW flow + 8*HW grad_flow."""
+    C, H, W = 1024, 38, 63
+    HW, F4 = H * W, C * H * W * 4
+    N = 16 if quick else 64
+    d = synth(N, C, H, W, 600, 1000, dev, max_px=96)
+    flow = ops.mv_pool(d["mv"])
+    og = torch.randn_like(d["key"])
+    gk = torch.empty_like(d["key"])
+    gf = torch.empty_like(flow)
+    ws = torch.empty(ops.A.load().lsfa_bilinear_sampler_backward_workspace_bytes(N, C, H, W, H, W), dtype=torch.uint8, device=dev)
+    for kern in ("gather", "scatter"):
+        st = 10 if kern == "gather" else 3
+        row("bwd warp: grad_key + grad_flow, fp32 NCHW (%s)" % kern, N, 3 * F4 + 16 * HW,
+            time_ms(lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel=kern), 2, st), pk)
+        row("bwd warp: grad_key only (SYM:320-321), fp32 NCHW (%s)" % kern, N, 2 * F4 + 8 * HW,
+            time_ms(lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, req_flow="null", workspace=ws, kernel=kern), 2, st), pk)
+    # smooth motion (every block moves by the same sub-cell vector): short, even lists
+    flow2 = torch.full_like(flow, 0.37)
+    row("bwd warp: grad_key + grad_flow, uniform flow (gather)", N, 3 * F4 + 16 * HW,
+        time_ms(lambda: ops.warp_backward(d["key"], flow2, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel="gather"), 2, 10), pk)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only-backward", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
+    if args.only_backward:
+        backward_rows(dev, pk, args.quick)
+        return
     s = torch.cuda.current_stream().cuda_stream
     C, H, W = 1024, 38, 63
     HW = H * W
@@ -166,6 +194,9 @@ def main():
     p = ops.PreparedAggregate(nh["key"], d4["mv"], flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
                               weight_mode="logits", logits=d4["logits"], layout="nhwc_bf16")
     row("cfg4 V2 bf16 NHWC 68x120 batch %d" % N4, N4, 4 * C * H4 * W4 * 2 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk)
+    del d4, nh, p
+    torch.cuda.empty_cache()
+    backward_rows(dev, pk, args.quick)
 
 
 if __name__ == "__main__":

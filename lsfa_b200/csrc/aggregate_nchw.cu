@@ -208,6 +208,24 @@ __global__ void __launch_bounds__(256) agg_records_kernel(const __grid_constant_
     pack_record(t, a, b);
     rec[2 * i] = a;
     rec[2 * i + 1] = b;
+    if (P.rowrange != nullptr) {
+      // key rows this pixel's (clamped) taps read: the streaming kernel loads only the rows its part needs
+      const int vf = n * P.parts + p / P.part_pix;
+      unsigned hi = (unsigned)(t.i10 / P.Wk) + 1u, lo_inv = (unsigned)(P.Hk - t.i00 / P.Wk);
+      const unsigned act = __activemask();
+      const int vf0 = __shfl_sync(act, vf, __ffs(act) - 1);
+      if (__all_sync(act, vf == vf0)) {          // the usual case: one atomic pair per warp
+        hi = __reduce_max_sync(act, hi);
+        lo_inv = __reduce_max_sync(act, lo_inv);
+        if ((threadIdx.x & 31) == __ffs(act) - 1) {
+          atomicMax(P.rowrange + 2 * vf, hi);
+          atomicMax(P.rowrange + 2 * vf + 1, lo_inv);
+        }
+      } else {
+        atomicMax(P.rowrange + 2 * vf, hi);
+        atomicMax(P.rowrange + 2 * vf + 1, lo_inv);
+      }
+    }
   }
 }
 
@@ -289,8 +307,12 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
   AggParams P = Pin;
   long long grid = sm_count();
   if (grid > P.items) grid = P.items;
-  if (P.sched) {  // the per-frame claim counters start every launch at zero (enqueue-only, no sync)
-    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * P.parts * sizeof(unsigned), st);
+  // planes cut into pixel parts: each part loads only the key rows its taps read (found by the pre-pass);
+  // needs whole rows / planes to stay 16-byte addressable
+  const bool trim = P.sched && P.records && P.parts > 1 && (P.HWk % 4) == 0 && getenv("LSFA_NO_ROW_TRIM") == nullptr;
+  P.rowrange = trim ? P.sched + (size_t)P.N * P.parts : nullptr;
+  if (P.sched) {  // the per-frame claim counters (and row ranges) start every launch at zero (enqueue-only, no sync)
+    cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * P.parts * sizeof(unsigned) * (trim ? 3 : 1), st);
     if (e != cudaSuccess) return e;
   }
   if (P.records) {  // pre-pass writes the records, the streaming kernel follows in stream order

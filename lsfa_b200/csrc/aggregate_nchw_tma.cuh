@@ -315,6 +315,9 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
           }
         }
       };
+      int range_vf = -1;
+      uint32_t range_b0 = 0u, range_b1 = 0u;
+      bool range_synced = false;
       auto issue_loads = [&](int s, int vf, int chunk) {
         const int n = vf / P.parts, part = vf - n * P.parts;
         const bool byp = has_bypass && __ldg(P.bypass + n) != 0;
@@ -324,15 +327,41 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
         // parts == 1: the K planes of a stream are one contiguous run; otherwise one copy per plane
         const uint32_t io_tx = P.parts == 1 ? P.io_bytes : (uint32_t)K * len_bytes;
         const size_t e0 = ((size_t)n * P.C + (size_t)chunk * K) * P.HW + pix0;
+        // key bytes of one plane this part needs: whole plane, or (row-trimmed) the 16-byte-rounded span of the
+        // rows its taps read - copied to the SAME smem offsets, so the tap offsets in the records stay valid
+        uint32_t kb0 = 0u, kb1 = (uint32_t)P.HWk * 4u;
+        const bool trimmed = P.rowrange != nullptr;
+        if (trimmed && !byp) {
+          if (vf != range_vf) {
+            if (P.pdl && !range_synced) {
+              pdl_wait();
+              range_synced = true;
+            }
+            range_vf = vf;
+            const unsigned hi = __ldcg(P.rowrange + 2 * vf), lo_inv = __ldcg(P.rowrange + 2 * vf + 1);
+            range_b0 = hi ? (((uint32_t)(P.Hk - (int)lo_inv) * (uint32_t)P.Wk * 4u) & ~15u) : 0u;
+            range_b1 = hi ? min((uint32_t)P.HWk * 4u, (hi * (uint32_t)P.Wk * 4u + 15u) & ~15u) : 0u;
+          }
+          kb0 = range_b0;
+          kb1 = range_b1;
+        }
+        const uint32_t key_tx = trimmed ? (uint32_t)K * (kb1 - kb0) : P.key_bytes;
         uint32_t bytes = has_cur ? io_tx : 0u;
-        if (!byp) bytes += P.key_bytes + (has_scale ? io_tx : 0u);
+        if (!byp) bytes += key_tx + (has_scale ? io_tx : 0u);
         desc[s].x = vf;
         desc[s].y = chunk;
         mbar_expect_tx(&full[s], bytes);              // release: the descriptor is visible with the data
         if (!byp) {
           const int kn = P.key_index ? __ldg(P.key_index + n) : n;
           const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
-          bulk_g2s(st, ksrc, P.key_bytes, &full[s]);
+          if (!trimmed) {
+            bulk_g2s(st, ksrc, P.key_bytes, &full[s]);
+          } else if (kb1 > kb0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+              bulk_g2s(st + (size_t)k * P.HWk * 4 + kb0, reinterpret_cast<const unsigned char*>(ksrc + (size_t)k * P.HWk) + kb0,
+                       kb1 - kb0, &full[s]);
+          }
         }
         if (P.parts == 1) {
           if (!byp && has_scale) bulk_g2s(st + P.off_scale, static_cast<const float*>(P.scale) + e0, P.io_bytes, &full[s]);

@@ -179,7 +179,7 @@ size_t records_ws_bytes(const LsfaAggArgs* a) {   // packed sampling records of 
 size_t sched_ws_bytes(const LsfaAggArgs* a) {
   if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   const size_t parts = ((size_t)a->H * a->W + 4319) / 4320;      // pixel parts of the all-TMA kernel (9 x 480)
-  return ((size_t)a->N * parts * sizeof(unsigned) + 15) / 16 * 16;
+  return ((size_t)a->N * parts * sizeof(unsigned) * 3 + 15) / 16 * 16;   // claim counters + 2 row-range words per part
 }
 
 int run_aggregate(const LsfaAggArgs* a, void* stream) {

@@ -61,6 +61,8 @@ struct AggParams {
   unsigned* sched;             // N zeroed counters for dynamic work claims, or NULL = static split
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
   int pdl;                     // launched as a programmatic dependent of the record pre-pass
+  unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:
+                               // [0] = last key row any tap of the part reads + 1, [1] = Hk - first such row; or NULL
 };
 
 // ---------------------------------------------------------------------------------------

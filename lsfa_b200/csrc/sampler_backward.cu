@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bwd_nchw_gather_kernel(const _
   }
   const int LS = P.L - LR;            // list slots kept in shared memory (>= 0 by planning)
   int cur_n = -1, s = 0;
-  unsigned ph = 0;
+  unsigned ph = 0, inside = 0u;   // bit j: every tap of slot j is inside the plane for the whole warp
   const unsigned og_plane_bytes = (unsigned)P.HW * 4u;
   auto flush = [&](int n) {
 #pragma unroll
@@ -431,6 +431,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bwd_nchw_gather_kernel(const _
           wy[j] = __uint_as_float(r.y);
           ot[j] = r.z;
           ob[j] = r.w;
+          const bool all4 = (r.z & r.w & 0x10001u) == 0x10001u || p >= P.HW;
+          inside = (inside & ~(1u << j)) | (__all_sync(0xffffffffu, all4) ? (1u << j) : 0u);
         }
       }
     }
@@ -451,10 +453,12 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bwd_nchw_gather_kernel(const _
             float v01 = *reinterpret_cast<const float*>(plane + ((ot[j] >> 16) & 0xfffcu));
             float v10 = *reinterpret_cast<const float*>(plane + (ob[j] & 0xfffcu));
             float v11 = *reinterpret_cast<const float*>(plane + ((ob[j] >> 16) & 0xfffcu));
-            v00 = (ot[j] & 1u) ? v00 : 0.f;
-            v01 = (ot[j] & 0x10000u) ? v01 : 0.f;
-            v10 = (ob[j] & 1u) ? v10 : 0.f;
-            v11 = (ob[j] & 0x10000u) ? v11 : 0.f;
+            if (!((inside >> j) & 1u)) {   // uniform per warp: some lane of this slot has a tap outside the plane
+              v00 = (ot[j] & 1u) ? v00 : 0.f;
+              v01 = (ot[j] & 0x10000u) ? v01 : 0.f;
+              v10 = (ob[j] & 1u) ? v10 : 0.f;
+              v11 = (ob[j] & 0x10000u) ? v11 : 0.f;
+            }
             const float d = v00 - v01 - v10 + v11;
             gya[j] -= og * (v01 - v11 + d * wx[j]);
             gxa[j] -= og * (v10 - v11 + d * wy[j]);
@@ -475,12 +479,27 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bwd_nchw_gather_kernel(const _
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.f;
 #pragma unroll
-        for (int e = 0; e < LR; ++e) {
-          if (e < m) {                                     // uniform branch; lanes with shorter lists are predicated off
-            const float w = lw[j][e];
-            const unsigned off = (lo[j][e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        for (int g = 0; g < LR; g += 3) {
+          if (g < m) {   // uniform branch; three entries at a time: all shared loads first, then the FMAs
+            float v[3][K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = fmaf(w, lds_f32_if(og_a + (unsigned)k * og_plane_bytes + off, w != 0.0f), acc[k]);
+            for (int u = 0; u < 3; ++u) {
+              const int e = g + u;
+              if (e < LR) {
+                const unsigned off = (lo[j][e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+#pragma unroll
+                for (int k = 0; k < K; ++k)   // lanes whose list is shorter have weight 0: predicated off, no access
+                  v[u][k] = lds_f32_if(og_a + (unsigned)k * og_plane_bytes + off, lw[j][e] != 0.0f);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int e = g + u;
+              if (e < LR) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(lw[j][e], v[u][k], acc[k]);
+              }
+            }
           }
         }
         for (int e = LR; e < m; ++e) {                     // the tail of long lists: entries in shared memory

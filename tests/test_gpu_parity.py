@@ -766,3 +766,25 @@ def test_torch_autograd_through_the_custom_ops(ops, cuda):
     want_k, want_f = O.warp_backward(data, flow, og)
     assert_close_f32(host(td.grad), want_k, scale=np.abs(want_k).max(), what="autograd grad_data")
     assert_close_f32(host(tf.grad), want_f, scale=np.abs(want_f).max(), what="autograd grad_flow")
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 68, 120), (2, 4, 100, 132), (4, 6, 60, 80)])
+def test_row_trimmed_key_loads_any_motion(ops, cuda, shape, monkeypatch):
+    """Planes cut into pixel parts load only the key rows each part's taps read (row ranges from the record
+    pre-pass).  Whatever the motion - huge flows, everything out of the plane, a still frame, bypass frames,
+    a shared key - the result must be bit-identical to the untrimmed kernel and pass the oracle gate."""
+    N, C, H, W = shape
+    d = make_case(90 + N, N, C, H, W, with_bypass=True, shared_key=(N == 4))
+    rng = np.random.default_rng(N)
+    flow = (rng.standard_normal((N, 2, H, W)) * 25).astype(np.float32)      # taps all over the plane
+    flow[0] = 0.0                                                          # still frame: each part needs its own rows only
+    if N > 2:
+        flow[2] = 500.0                                                    # everything out of the plane
+        flow[2, :, H // 2:] = rng.uniform(-3, 3, size=(2, H - H // 2, W))   # ... except the second part: local motion
+    d["flow"] = flow
+    want = oracle_fused(d, O.W_LOGITS)
+    got = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=3)
+    assert_close_f32(host(got), want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="trimmed %s" % (shape,))
+    monkeypatch.setenv("LSFA_NO_ROW_TRIM", "1")
+    full = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=3)
+    assert torch.equal(got, full)

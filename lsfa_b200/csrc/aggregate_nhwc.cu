@@ -35,6 +35,10 @@ constexpr int kTileW = 8;
 constexpr int kTilePix = kTileH * kTileW;
 constexpr int kStreamWarps = kTileW;                       // one warp per tile column
 constexpr int kNhwcTileThreads = (kStreamWarps + 1) * 32;   // + the record warp
+#ifndef LSFA_NHWC_PREFETCH
+#define LSFA_NHWC_PREFETCH 1
+#endif
+constexpr bool kNhwcPrefetch = LSFA_NHWC_PREFETCH != 0;
 
 struct __align__(16) TileRec {
   float w00, w01, w10, w11;   // tap weights, blend weight folded in
@@ -200,6 +204,40 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
             const bool two = c + CSTEP + lane * L < P.C;
             const uint4 z = make_uint4(0, 0, 0, 0);
             uint4 v[2][6];
+            if (kNhwcPrefetch) {
+              // L2 prefetch of the NEXT batch (same pixel, next channel chunks; or the first chunks of the next
+              // row's pixel): the loads of that batch then wait an L2 round trip instead of a DRAM one, with
+              // no registers held meanwhile.  The streaming warps were latency bound (long_scoreboard 4.3/issue).
+              if (c + 2 * CSTEP + lane * L < P.C) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int co = (2 + h) * CSTEP;
+                  if (h == 1 && !(c + 3 * CSTEP + lane * L < P.C)) break;
+                  if (!bp) {
+                    prefetch_l2(k00 + co); prefetch_l2(k01 + co); prefetch_l2(k10 + co); prefetch_l2(k11 + co);
+                    if (has_scale) prefetch_l2(ps + co);
+                  }
+                  if (has_cur) prefetch_l2(pc + co);
+                }
+              } else if (r + 1 < kTileH) {
+                const TileRec& nx = cur_recs[(r + 1) * kTileW + warp];
+                if (nx.use & (1 << 8)) {
+                  const bool nbp = (nx.use & (1 << 9)) != 0;
+                  const size_t nob = obase + (size_t)P.W * P.C;
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const int co = h * CSTEP;
+                    if (!(co + lane * L < P.C)) break;
+                    if (!nbp) {
+                      prefetch_l2(kbase + (size_t)nx.i00 * P.C + co); prefetch_l2(kbase + (size_t)nx.i01 * P.C + co);
+                      prefetch_l2(kbase + (size_t)nx.i10 * P.C + co); prefetch_l2(kbase + (size_t)nx.i11 * P.C + co);
+                      if (has_scale) prefetch_l2(scale + nob + co);
+                    }
+                    if (has_cur) prefetch_l2(cur + nob + co);
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int co = h * CSTEP;            // compile-time offset from the running pointers

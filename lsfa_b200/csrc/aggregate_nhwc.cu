@@ -30,7 +30,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // softmax) never sits on the streaming warps' critical path.  Channels are walked in chunks of
 // kChunkVecs 16-byte vectors per pixel so a tile pass touches ~45 key pixels x 512 B: the x- and
 // y-neighbour taps of the 4-tap stencil are re-read while still in L1.
-constexpr int kTileH = 4;
+#ifndef LSFA_NHWC_TILE_H
+#define LSFA_NHWC_TILE_H 4
+#endif
+constexpr int kTileH = LSFA_NHWC_TILE_H;   // rows per tile (multiple of 4: the record warp builds 32 pixels per pass)
 constexpr int kTileW = 8;
 constexpr int kTilePix = kTileH * kTileW;
 constexpr int kStreamWarps = kTileW;                       // one warp per tile column
@@ -74,7 +77,8 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
     const int tx = (int)(tile % tiles_x);
     const int ty = (int)((tile / tiles_x) % tiles_y);
     const int n = (int)(tile / ((long long)tiles_x * tiles_y));
-    const int r = lane / kTileW, cx = lane % kTileW;
+   for (int pass = 0; pass < kTilePix / 32; ++pass) {   // one lane per pixel, 32 pixels per pass
+    const int r = pass * (32 / kTileW) + lane / kTileW, cx = lane % kTileW;
     const int y = ty * kTileH + r, x = tx * kTileW + cx;
     TileRec rec;
     rec.w00 = rec.w01 = rec.w10 = rec.w11 = rec.ww = rec.wc = 0.f;
@@ -95,7 +99,8 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
         rec.i00 = t.i00; rec.i01 = t.i01; rec.i10 = t.i10; rec.i11 = t.i11;
       }
     }
-    dst[lane] = rec;
+    dst[pass * 32 + lane] = rec;
+   }
   };
 
   long long tile = blockIdx.x;

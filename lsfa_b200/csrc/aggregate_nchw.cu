@@ -271,7 +271,8 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   if ((long long)part_pix * (parts - 1) >= P.HW) return false;   // every part must be non-empty
   const bool has_scale = var == kVarScale || var == kVarScaleCur;
   // res variant: pooled residual of the frame part [3][part_pix] + the rnet_conv0 table [C] x (w0,w1,w2,b)
-  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 + (size_t)P.C * 16 : 0;
+  // (up to 5 pixel slots per thread keep the residual in registers: no [3][part_pix] array)
+  const size_t res_bytes = var == kVarResCur ? (ppt <= 5 ? 0 : (size_t)3 * part_pix * 4) + (size_t)P.C * 16 : 0;
   const int io_plane = parts == 1 ? P.HW : part_pix;             // elements per plane slice in a stage
   const size_t pad = (((size_t)part_pix - (parts == 1 ? P.HW : 0)) * 4 + 127) / 128 * 128;
   const int prefer[2] = {2, 1};
@@ -353,7 +354,7 @@ bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
   if (part_pix >= P.HW) return false;
   if (sm_count() < 2) return false;
   const bool has_scale = var == kVarScale || var == kVarScaleCur;
-  const size_t res_bytes = var == kVarResCur ? (size_t)3 * part_pix * 4 + (size_t)P.C * 16 : 0;
+  const size_t res_bytes = var == kVarResCur ? (ppt <= 5 ? 0 : (size_t)3 * part_pix * 4) + (size_t)P.C * 16 : 0;
   const int K = 1;
   const unsigned key_bytes = (unsigned)((size_t)K * P.HWk * 4), io_bytes = (unsigned)((size_t)K * part_pix * 4);
   const unsigned off_scale = (key_bytes + 127u) / 128u * 128u;

@@ -62,6 +62,13 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
   const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
   (void)ww;
   constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
+  // pooled residual of this thread's pixels (a10): in registers for up to 5 slots - three shared-memory reads per
+  // element less on the variant that is shared-memory-bandwidth bound; larger parts keep it in smem
+  constexpr bool RES_REG = has_res && PPT <= 5;
+  constexpr int RRN = RES_REG ? PPT : 1;
+  float rr0[RRN], rr1[RRN], rr2[RRN];
+#pragma unroll
+  for (int j = 0; j < RRN; ++j) rr0[j] = rr1[j] = rr2[j] = 0.f;
 
   if (has_res) {   // the 1x1 conv's weights (SYM:66) sit in smem: per-item global loads would stall every item
     for (int c = tid; c < P.C; c += kTmaConsumers)
@@ -118,9 +125,15 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           if (has_res) {
             const int p = pix0 + tid + j * kTmaConsumers;
             if (p < pend && !byp) {
+              if (RES_REG) {
+                rr0[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
+                rr1[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
+                rr2[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
+              } else {
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-                res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+                for (int k = 0; k < 3; ++k)
+                  res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+              }
             }
           }
         }
@@ -166,9 +179,15 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
               o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
               o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
               if (has_res) {
+                if (RES_REG) {
+                  rr0[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
+                  rr1[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
+                  rr2[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                  res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+                  for (int k = 0; k < 3; ++k)
+                    res_s[k * (PPT * kTmaConsumers) + (p - pix0)] = __ldg(P.res + ((size_t)n * 3 + k) * P.HW + p);
+                }
               }
             }
           }
@@ -217,8 +236,11 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
               if (has_scale) v *= sc[g];
               if (has_res) {
                 const int q = tid + j * kTmaConsumers;
-                v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
-                                          res_s[2 * PPT * kTmaConsumers + q]), v);
+                if (RES_REG)
+                  v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, rr0[j % RRN], rr1[j % RRN], rr2[j % RRN]), v);
+                else
+                  v = fmaf(ww[j], rnet_term(rw0, rw1, rw2, rb, res_s[q], res_s[PPT * kTmaConsumers + q],
+                                            res_s[2 * PPT * kTmaConsumers + q]), v);
               }
               const float o = has_cur ? fmaf(wc[j], cu[g], v) : v;
               if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
@@ -250,7 +272,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   volatile int2* desc = reinterpret_cast<volatile int2*>(smem_raw + 128);   // (frame, chunk) of each stage; frame < 0 = stop
   unsigned char* ring = smem_raw + kTmaHeaderBytes;
   float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);  // [3][PPT*480]
-  float4* rnet_s = reinterpret_cast<float4*>(res_s + 3 * PPT * kTmaConsumers);       // [C] (w0,w1,w2,b), res variant only
+  float4* rnet_s = reinterpret_cast<float4*>(res_s + (PPT <= 5 ? 0 : 3 * PPT * kTmaConsumers));       // [C] (w0,w1,w2,b), res variant only
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;

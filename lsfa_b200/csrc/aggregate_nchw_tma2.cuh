@@ -81,7 +81,7 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
   volatile int2* desc = reinterpret_cast<volatile int2*>(smem_raw + 256);
   unsigned char* ring = smem_raw + kTma2HeaderBytes;
   float* res_s = reinterpret_cast<float*>(ring + (size_t)P.stages * P.stage_bytes);
-  float4* rnet_s = reinterpret_cast<float4*>(res_s + 3 * PPT * kTmaConsumers);
+  float4* rnet_s = reinterpret_cast<float4*>(res_s + (PPT <= 5 ? 0 : 3 * PPT * kTmaConsumers));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;

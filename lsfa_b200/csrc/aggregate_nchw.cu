@@ -306,6 +306,17 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
 
 cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
+  if (getenv("LSFA_TMA_STATIC")) P.sched = nullptr;          // experiment knobs (ablations)
+  if (getenv("LSFA_TMA_NO_RECORDS")) P.records = nullptr;
+  {
+    // share of the items handed out dynamically at the end (the rest is a static contiguous split)
+    int pct = kTmaPoolPercent;
+    if (const char* e = getenv("LSFA_TMA_POOL_PCT")) pct = atoi(e);
+    if (pct < 0) pct = 0;
+    if (pct > 100) pct = 100;
+    P.pool_base = P.items - P.items * pct / 100;
+    P.pool_base -= P.pool_base % kTmaClaim;                  // claims stay aligned to the claim size
+  }
   long long grid = sm_count();
   if (grid > P.items) grid = P.items;
   // planes cut into pixel parts: each part loads only the key rows its taps read (found by the pre-pass);

@@ -14,8 +14,9 @@
 // Pipeline (S stages, S >= 2):  full[s]  : producer -> consumers   (TMA bytes landed)
 //                               done[s]  : consumers -> producer   (stage computed, out in smem)
 //   producer: wait done[c] -> TMA-store stage c -> wait_group.read -> TMA-load the next item into it
-// Work is handed out dynamically (per-frame queues in a caller-supplied scratch) so that SMs
-// with more bandwidth do more items; each stage carries its (frame, chunk) descriptor in smem.
+// Work: a static contiguous share per CTA followed by a dynamically claimed pool (one counter in a
+// caller-supplied scratch) so that SMs that finish early take the tail; each stage carries its
+// (frame, chunk) descriptor in smem.
 #pragma once
 #include "aggregate_nchw_plane.cuh"
 
@@ -37,6 +38,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 constexpr int kTmaHeaderBytes = 256;   // 16 mbarriers + one item descriptor per stage
 constexpr int kTmaClaim = 4;           // items per dynamic claim (4 x ~1.8 us of work)
+constexpr int kTmaPoolPercent = 10;    // share of the items left to the dynamic pool (see the producer)
 
 // The 15 consumer warps of both all-TMA kernels (single CTA and 2-CTA cluster): shared-memory-only
 // work on the stages the producer warp fills.  fixed_part < 0: the stage descriptor carries a virtual
@@ -290,51 +292,35 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   if (warp == kTmaConsumerWarps) {
     // =========================== producer warp (one elected lane) ===========================
     if ((tid & 31) == 0) {
-      // ---- work source: dynamic per-frame queues (sched != NULL) or a static contiguous range ----
-      // Dynamic: every frame f has a counter of claimed channel chunks.  A CTA stays on its frame
-      // (the consumers' sampling records are per frame) and claims kTmaClaim chunks at a time;
-      // when the frame is exhausted it hops to the next one.  SMs that see more bandwidth simply
-      // claim more, which removes the 20-25% tail a static split shows on B200 (unequal GPCs).
-      // A "virtual frame" is (frame, pixel part): planes larger than PPT*480 pixels are cut into
-      // parts, each with its own sampling records, queue and slice of the scale/cur/out streams.
+      // ---- work source: a static contiguous share per CTA, then a shared pool claimed dynamically ----
+      // Linear item index = virtual frame * chunks + chunk; a "virtual frame" is (frame, pixel part): planes
+      // larger than PPT*480 pixels are cut into parts, each with its own sampling records and slice of the
+      // scale/cur/out streams.  Items [0, pool_base) are split evenly and contiguously over the CTAs (no
+      // atomics, a CTA stays on one frame for ~hundreds of items, so its per-frame records are rebuilt once or
+      // twice); items [pool_base, items) are claimed kTmaClaim at a time from ONE counter, so SMs that finish
+      // early (unequal GPCs, bypass frames, row-trimmed parts) take the tail.  pool_base == items: purely
+      // static (no scratch given); pool_base == 0: purely dynamic.
       unsigned* sched = P.sched;
-      const int NV = P.N * P.parts;
-      int f = (int)(((long long)blockIdx.x * NV) / gridDim.x), c = 0, cend = 0, hops = 0;
-      if (sched == nullptr) {                         // static: items [i0, i1) of the (virtual frame, chunk) grid
-        const long long i0 = P.items * (long long)blockIdx.x / gridDim.x;
-        const long long i1 = P.items * (long long)(blockIdx.x + 1) / gridDim.x;
-        f = (int)(i0 / P.chunks);
-        c = (int)(i0 - (long long)f * P.chunks);
-        hops = (int)(i1 - i0);                        // static mode: items left
-        cend = P.chunks;
-      }
+      const long long pool_base = sched ? P.pool_base : P.items;
+      long long lin = pool_base * (long long)blockIdx.x / gridDim.x;
+      long long lin_end = pool_base * (long long)(blockIdx.x + 1) / gridDim.x;
+      bool pool_open = sched != nullptr && pool_base < P.items;
       auto next_item = [&](int& n, int& chunk) -> bool {
-        if (sched == nullptr) {
-          if (hops <= 0) return false;
-          --hops;
-          n = f;
-          chunk = c;
-          if (++c == P.chunks) {
-            c = 0;
-            ++f;
-          }
-          return true;
-        }
         while (true) {
-          if (c < cend) {
-            n = f;
-            chunk = c++;
+          if (lin < lin_end) {
+            n = (int)(lin / P.chunks);
+            chunk = (int)(lin - (long long)n * P.chunks);
+            ++lin;
             return true;
           }
-          if (hops >= NV) return false;               // every queue has been seen exhausted
-          const int got = (int)atomicAdd(sched + f, (unsigned)kTmaClaim);
-          if (got < P.chunks) {
-            c = got;
-            cend = min(got + kTmaClaim, P.chunks);
-          } else {
-            f = (f + 1 == NV) ? 0 : f + 1;
-            ++hops;
+          if (!pool_open) return false;
+          const long long got = pool_base + (long long)atomicAdd(sched, (unsigned)kTmaClaim);
+          if (got >= P.items) {
+            pool_open = false;
+            return false;
           }
+          lin = got;
+          lin_end = min(got + (long long)kTmaClaim, P.items);
         }
       };
       int range_vf = -1;

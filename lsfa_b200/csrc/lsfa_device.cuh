@@ -58,7 +58,8 @@ struct AggParams {
   long long items;
   // stage layout of the all-TMA kernel: [key planes | scale chunk | cur/out chunk]
   unsigned key_bytes, io_bytes, off_scale, off_io;
-  unsigned* sched;             // N zeroed counters for dynamic work claims, or NULL = static split
+  unsigned* sched;             // zeroed counter(s) for dynamic work claims, or NULL = static split
+  long long pool_base;         // all-TMA kernel: items [0,pool_base) are split statically, the rest claimed from sched[0]
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
   int pdl;                     // launched as a programmatic dependent of the record pre-pass
   unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:

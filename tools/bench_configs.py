@@ -117,6 +117,14 @@ def main():
     row("cfg1 V0 fused warp only, raw MV, static split (no scratch)", N, 2 * F4 + 32 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
     p = ops.PreparedAggregate(d["key"], flow, flow_kind="flow")
     row("cfg1 V0 fused warp only, flow given", N, 2 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    p = ops.PreparedAggregate(d["key"], flow, flow_kind="flow", workspace=False)
+    row("cfg1 V0 fused warp only, flow given, static split", N, 2 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    p = ops.PreparedAggregate(d["key"], grid, flow_kind="grid")
+    row("cfg1 V0 fused warp only, grid given", N, 2 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
+    p = ops.PreparedAggregate(d["key"], flow, flow_kind="flow", scale_map=d["scale_map"])
+    row("batch path: warp x scale (SYM:678-680), flow given", N, 3 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk)
+    p = ops.PreparedAggregate(d["key"], flow, flow_kind="flow", scale_map=d["scale_map"], workspace=False)
+    row("batch path: warp x scale, static split", N, 3 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk, "ablation")
     p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], res=d["res"], rnet_w=d["rnet_w"],
                               rnet_b=d["rnet_b"], weight_mode="add")
     row("V1 shipped non-key path: warp + rnet(res) + cur", N, 3 * F4 + 32 * HW + 12 * HW + 16384, time_ms(lambda: p.run(s)), pk)

@@ -289,7 +289,10 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(frames), "kernel": "agg_nchw_tma_kernel<K=2,PPT=5,ScaleCur>",
                 "note": "launch_ms is one whole step = agg_records_kernel (index-math pre-pass, ~3 us) + the dominant "
-                        "streaming kernel, so `achieved` slightly understates the dominant kernel on its own",
+                        "streaming kernel, so `achieved` slightly understates the dominant kernel on its own. `peak` is "
+                        "the driver-measured torch copy bandwidth (MEASURED_PEAKS.json: b.copy_(a), 1 Gi bf16), not the "
+                        "hardware limit: a TMA-in/TMA-out kernel whose traffic is 3/4 reads can exceed it (frac > 1); "
+                        "frac_of_nominal_8TBs and ncu's dram__throughput (profiles/) are the conservative views",
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 

@@ -21,6 +21,7 @@
 //     the producer TMA-stores them (cp.reduce.async.bulk ... add.f32 for req = kAddTo).
 //   HBM: out_grad once, data once (only when d/d(grid) is wanted), grad_data once: 3F (or 2F).
 //   grad_data is deterministic (fixed summation order) unless a list overflowed.
+#include <cstdlib>
 #include <cstring>
 
 #include "aggregate_nchw_tma.cuh"
@@ -49,6 +50,7 @@ struct BwdParams {
   uint4* ovf;                // {n, q, p, weight bits}
   unsigned ovf_cap;
   unsigned* sched;
+  long long pool_base;       // items [0,pool_base) split statically, the rest claimed from sched[0]
 };
 
 struct BwdTaps {
@@ -250,42 +252,30 @@ __global__ void __launch_bounds__(kTmaThreads, 1) bwd_nchw_gather_kernel(const _
   if (warp == kTmaConsumerWarps) {
     // =========================== producer warp (one elected lane) ===========================
     if ((tid & 31) == 0) {
+      // work source, as in agg_nchw_tma_kernel: a static contiguous share of the (frame, chunk) items per CTA
+      // (few frame changes: a change reloads the lists), then a pool claimed kTmaClaim at a time from one counter
       unsigned* sched = P.sched;
-      int f = (int)(((long long)blockIdx.x * P.N) / gridDim.x), c = 0, cend = 0, hops = 0;
       const long long items = (long long)P.N * P.chunks;
-      if (sched == nullptr) {
-        const long long i0 = items * (long long)blockIdx.x / gridDim.x, i1 = items * (long long)(blockIdx.x + 1) / gridDim.x;
-        f = (int)(i0 / P.chunks);
-        c = (int)(i0 - (long long)f * P.chunks);
-        hops = (int)(i1 - i0);
-      }
+      const long long pool_base = sched ? P.pool_base : items;
+      long long lin = pool_base * (long long)blockIdx.x / gridDim.x;
+      long long lin_end = pool_base * (long long)(blockIdx.x + 1) / gridDim.x;
+      bool pool_open = sched != nullptr && pool_base < items;
       auto next_item = [&](int& n, int& chunk) -> bool {
-        if (sched == nullptr) {
-          if (hops <= 0) return false;
-          --hops;
-          n = f;
-          chunk = c;
-          if (++c == P.chunks) {
-            c = 0;
-            ++f;
-          }
-          return true;
-        }
         while (true) {
-          if (c < cend) {
-            n = f;
-            chunk = c++;
+          if (lin < lin_end) {
+            n = (int)(lin / P.chunks);
+            chunk = (int)(lin - (long long)n * P.chunks);
+            ++lin;
             return true;
           }
-          if (hops >= P.N) return false;
-          const int got = (int)atomicAdd(sched + f, (unsigned)kTmaClaim);
-          if (got < P.chunks) {
-            c = got;
-            cend = min(got + kTmaClaim, P.chunks);
-          } else {
-            f = (f + 1 == P.N) ? 0 : f + 1;
-            ++hops;
+          if (!pool_open) return false;
+          const long long got = pool_base + (long long)atomicAdd(sched, (unsigned)kTmaClaim);
+          if (got >= items) {
+            pool_open = false;
+            return false;
           }
+          lin = got;
+          lin_end = min(got + (long long)kTmaClaim, items);
         }
       };
       auto issue_loads = [&](int s, int n, int chunk) {
@@ -656,6 +646,13 @@ cudaError_t launch_sampler_backward(const float* data, const float* coords, int 
     long long grid = sm_count;
     const long long items = (long long)P.N * P.chunks;
     if (grid > items) grid = items;
+    {
+      int pct = kTmaPoolPercent;
+      if (const char* e = getenv("LSFA_TMA_POOL_PCT")) pct = atoi(e);
+      pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
+      P.pool_base = items - items * pct / 100;
+      P.pool_base -= P.pool_base % kTmaClaim;
+    }
     if (P.K == 2 && ppt == 5) e = launch_gather<2, 5>(P, smem_main, (int)grid, st);
     else if (P.K == 2) e = launch_gather<2, 9>(P, smem_main, (int)grid, st);
     else if (ppt == 5) e = launch_gather<1, 5>(P, smem_main, (int)grid, st);

@@ -72,3 +72,17 @@ def test_backward_known_answers():
     out = O.grid_generator_warp_backward(g)
     assert np.array_equal(out[:, 0], g[:, 0] / np.float32(31.0)) and np.array_equal(out[:, 1], g[:, 1] / np.float32(18.5))
     assert np.array_equal(P.grid_generator_warp_backward(g), out)
+
+
+def test_backward_oracle_vs_committed_torch_autograd_fixture():
+    """tests/golden/backward_small.npz was minted by tools/make_golden_backward.py from torch autograd of
+    grid_sample(align_corners=True) - an implementation independent of this oracle."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "backward_small.npz"))
+    gk, gg = O.bilinear_sampler_backward(g["key"], g["grid"], g["out_grad"])
+    assert np.abs(gk - g["grad_key"]).max() <= 2e-6 * np.abs(g["grad_key"]).max()
+    assert np.abs(gg - g["grad_grid"]).max() <= 2e-6 * np.abs(g["grad_grid"]).max()
+    gk2, gf = O.warp_backward(g["key"], g["flow"], g["out_grad"])
+    assert np.array_equal(gk2, gk)
+    assert np.abs(gf - g["grad_flow"]).max() <= 2e-6 * np.abs(g["grad_flow"]).max()
+    assert np.abs(O.warp(g["key"], g["flow"]) - g["out"]).max() <= 2e-6 * np.abs(g["out"]).max()

@@ -790,3 +790,17 @@ def test_row_trimmed_key_loads_any_motion(ops, cuda, shape, monkeypatch):
     monkeypatch.setenv("LSFA_NO_ROW_TRIM", "1")
     full = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=3)
     assert torch.equal(got, full)
+
+
+def test_backward_golden_fixture_from_torch_autograd(ops, cuda):
+    """Committed vectors minted from an independent implementation (tools/make_golden_backward.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "backward_small.npz"))
+    for kernel in ("gather", "scatter"):
+        gk, gf = ops.warp_backward(dev(g["key"], cuda), dev(g["flow"], cuda), dev(g["out_grad"], cuda), kernel=kernel)
+        assert np.abs(host(gk) - g["grad_key"]).max() <= 4e-6 * np.abs(g["grad_key"]).max(), kernel
+        assert np.abs(host(gf) - g["grad_flow"]).max() <= 4e-6 * np.abs(g["grad_flow"]).max(), kernel
+    gk, gg = ops.BilinearSampler_backward(dev(g["key"], cuda), dev(g["grid"], cuda), dev(g["out_grad"], cuda))
+    assert np.abs(host(gg) - g["grad_grid"]).max() <= 4e-6 * np.abs(g["grad_grid"]).max()
+    out = ops.BilinearSampler(dev(g["key"], cuda), dev(g["grid"], cuda))
+    assert np.abs(host(out) - g["out"]).max() <= 4e-6 * np.abs(g["out"]).max()

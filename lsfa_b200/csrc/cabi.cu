@@ -19,6 +19,10 @@ cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t 
 cudaError_t launch_agg_nchw_generic(const AggParams& P, cudaStream_t st);
 cudaError_t launch_cosine_logits_nchw(const float* ew, const float* ec, float* logits, int N, int E,
                                       int HW, cudaStream_t st);
+// cosine_nchw.cu
+size_t cosine_tma_workspace_bytes(int N, int E, int HW);
+cudaError_t launch_cosine_logits_nchw_tma(const float* ew, const float* ec, float* logits, int N, int E, int HW,
+                                          void* scratch, size_t scratch_bytes, cudaStream_t st);
 // aggregate_nhwc.cu
 cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st);
 cudaError_t launch_cosine_logits_nhwc(const void* ew, const void* ec, float* logits, int N, int E,
@@ -172,6 +176,10 @@ size_t cosine_ws_bytes(const LsfaAggArgs* a) {
   if (a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   return (size_t)a->N * 2 * a->H * a->W * sizeof(float);
 }
+size_t cosine_partials_ws_bytes(const LsfaAggArgs* a) {   // partial sums of the all-TMA cosine pre-pass (optional)
+  if (cosine_ws_bytes(a) == 0 || a->E <= 0) return 0;
+  return (lsfa::cosine_tma_workspace_bytes(a->N, a->E, a->H * a->W) + 15) / 16 * 16;
+}
 size_t records_ws_bytes(const LsfaAggArgs* a) {   // packed sampling records of the pre-pass: 32 B per output pixel
   if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   return (size_t)a->N * a->H * a->W * 32;
@@ -197,15 +205,22 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
         return fail(LSFA_E_BADARG, "LSFA_W_COSINE in NCHW needs a workspace of %zu bytes", need);
       if (reinterpret_cast<uintptr_t>(a->workspace) % 4) return fail(LSFA_E_ALIGN, "workspace must be 4-byte aligned");
       float* lg = static_cast<float*>(a->workspace);
-      rc = cuda_result(lsfa::launch_cosine_logits_nchw(static_cast<const float*>(a->emb_warp),
-                                                       static_cast<const float*>(a->emb_cur), lg, a->N,
-                                                       a->E, P.HW, st),
-                       "cosine_logits_nchw launch");
+      // with the full workspace: all-TMA pre-pass (deterministic partial sums); else the LDG kernel
+      const size_t lg_b = (need + 15) / 16 * 16, part_b = cosine_partials_ws_bytes(a);
+      cudaError_t ce = cudaErrorNotSupported;
+      if (part_b && a->workspace_bytes >= lg_b + part_b && (reinterpret_cast<uintptr_t>(a->workspace) % 16) == 0 &&
+          a->force_generic != 1)
+        ce = lsfa::launch_cosine_logits_nchw_tma(static_cast<const float*>(a->emb_warp), static_cast<const float*>(a->emb_cur),
+                                                 lg, a->N, a->E, P.HW, static_cast<char*>(a->workspace) + lg_b, part_b, st);
+      if (ce == cudaErrorNotSupported)
+        ce = lsfa::launch_cosine_logits_nchw(static_cast<const float*>(a->emb_warp), static_cast<const float*>(a->emb_cur), lg,
+                                             a->N, a->E, P.HW, st);
+      rc = cuda_result(ce, "cosine_logits_nchw launch");
       if (rc != LSFA_OK) return rc;
       P.logits = lg;
     }
     // optional scratch for dynamic work claiming (all-TMA kernel); without it the split is static
-    const size_t cos_b = (cosine_ws_bytes(a) + 15) / 16 * 16;
+    const size_t cos_b = (cosine_ws_bytes(a) + 15) / 16 * 16 + cosine_partials_ws_bytes(a);
     const size_t ws_need = cos_b + sched_ws_bytes(a) + records_ws_bytes(a);
     if (a->workspace && a->workspace_bytes >= ws_need && (reinterpret_cast<uintptr_t>(a->workspace) % 16) == 0) {
       char* ws = static_cast<char*>(a->workspace);
@@ -332,14 +347,18 @@ int lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream) {
 }
 
 size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) {
-  return (cosine_ws_bytes(args) + 15) / 16 * 16 + sched_ws_bytes(args) + records_ws_bytes(args);
+  return (cosine_ws_bytes(args) + 15) / 16 * 16 + cosine_partials_ws_bytes(args) + sched_ws_bytes(args) + records_ws_bytes(args);
 }
 
 int lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args) {
   if (!args || args->req == LSFA_REQ_NULL) return 0;
   if (args->layout != LSFA_LAYOUT_NCHW_F32) return 1;
   int n = 1;
-  if (args->weight_mode == LSFA_W_COSINE) ++n;                       // cosine-logit pre-pass
+  if (args->weight_mode == LSFA_W_COSINE) {                          // cosine-logit pre-pass (+ its finalize when all-TMA)
+    ++n;
+    const size_t full = lsfa_warp_scale_aggregate_workspace_bytes(args);
+    if (cosine_partials_ws_bytes(args) && args->workspace && args->workspace_bytes >= full && args->force_generic != 1) ++n;
+  }
   const size_t need = lsfa_warp_scale_aggregate_workspace_bytes(args);
   if (args->workspace && args->workspace_bytes >= need && args->force_generic != 1 && args->force_generic != 2)
     ++n;                                                             // record pre-pass (all-TMA kernel)

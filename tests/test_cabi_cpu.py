@@ -68,7 +68,9 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_SHAPE             # 100x64 pools to 7x4
     a = A.new_args(N=1, C=8, H=4, W=4, req=A.REQ_WRITE, key=16, flow=16, out=16, weight_mode=A.W_COSINE,
                    cur=16, emb_warp=16, emb_cur=16, E=32)
-    assert lib.lsfa_warp_scale_aggregate_workspace_bytes(a) == 1 * 2 * 4 * 4 * 4 + 16 + 16 * 32   # logits + claim counters + records
+    # logits + partial sums of the all-TMA cosine pre-pass (16 channel pairs -> 16 CTAs -> 16 slots x 3 sums x 16 px)
+    # + claim counters / row ranges + records
+    assert lib.lsfa_warp_scale_aggregate_workspace_bytes(a) == 1 * 2 * 4 * 4 * 4 + 16 * 3 * 16 * 4 + 16 + 16 * 32
     assert lib.lsfa_warp_scale_aggregate_num_launches(a) == 2
     assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_BADARG            # workspace missing
     a.layout = A.LAYOUT_NHWC_F32

@@ -804,3 +804,23 @@ def test_backward_golden_fixture_from_torch_autograd(ops, cuda):
     assert np.abs(host(gg) - g["grad_grid"]).max() <= 4e-6 * np.abs(g["grad_grid"]).max()
     out = ops.BilinearSampler(dev(g["key"], cuda), dev(g["grid"], cuda))
     assert np.abs(host(out) - g["out"]).max() <= 4e-6 * np.abs(g["out"]).max()
+
+
+@pytest.mark.parametrize("N,E,H,W", [(3, 2048, 38, 63), (1, 512, 38, 63), (5, 6, 10, 12), (2, 64, 60, 72)])
+def test_cosine_prepass_all_tma_vs_ldg_and_oracle(ops, cuda, N, E, H, W):
+    """Fgfa weights in NCHW (SYM:111-116,132-148): with the full workspace the cosine pre-pass is the all-TMA kernel
+    (static split, one partial per CTA and frame, slots added in order); it must agree with the LDG pre-pass
+    (force_generic=1 pins it), be bit-identical from run to run, and pass the oracle gate.  N=1 spreads one frame
+    over every CTA (many partial slots)."""
+    d = make_case(300 + N, N, 8, H, W, E=E)
+    want = oracle_fused(d, O.W_COSINE)
+    scale = max(np.abs(d["key"]).max(), np.abs(d["cur"]).max())
+    got = run_fused(ops, cuda, d, "cosine", "nchw")
+    again = run_fused(ops, cuda, d, "cosine", "nchw")
+    ldg = run_fused(ops, cuda, d, "cosine", "nchw", force_generic=1)
+    assert torch.equal(got, again)
+    assert_close_f32(host(got), want, scale=scale, what="cosine all-TMA pre-pass")
+    assert_close_f32(host(ldg), want, scale=scale, what="cosine LDG pre-pass")
+    assert ops.num_launches(key=dev(d["key"], cuda), flow=dev(d["flow"], cuda), cur=dev(d["cur"], cuda),
+                            scale_map=dev(d["scale_map"], cuda), weight_mode="cosine", emb_warp=dev(d["emb_warp"], cuda),
+                            emb_cur=dev(d["emb_cur"], cuda)) == 4     # cosine partials + finalize + records + fused

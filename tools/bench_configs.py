@@ -88,15 +88,36 @@ def backward_rows(dev, pk, quick):
         time_ms(lambda: ops.warp_backward(d["key"], flow2, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel="gather"), 2, 10), pk)
 
 
+def cosine_rows(dev, pk, Nc):
+    C, H, W, E = 1024, 38, 63, 2048
+    HW, F4 = H * W, C * H * W * 4
+    d = synth(Nc, C, H, W, 600, 1000, dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    ew = torch.randn((Nc, E, H, W), device=dev, generator=g)
+    ec = torch.randn((Nc, E, H, W), device=dev, generator=g)
+    s = torch.cuda.current_stream().cuda_stream
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                              weight_mode="cosine", emb_warp=ew, emb_cur=ec)
+    row("V3 cosine (Fgfa) fp32 NCHW batch %d: all-TMA cosine pre-pass + fused" % Nc, Nc, 4 * F4 + 40 * HW + 2 * E * HW * 4,
+        time_ms(lambda: p.run(s)), pk, "%d launches" % p.launches)
+    lg = torch.empty((Nc, 2, H, W), device=dev)
+    row("cosine logits alone (LDG kernel, lsfa_cosine_logits)", Nc, 2 * E * HW * 4 + 8 * HW,
+        time_ms(lambda: ops.cosine_logits(ew, ec)), pk)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only-backward", action="store_true")
+    ap.add_argument("--only-cosine", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
     if args.only_backward:
         backward_rows(dev, pk, args.quick)
+        return
+    if args.only_cosine:
+        cosine_rows(dev, pk, 64)
         return
     s = torch.cuda.current_stream().cuda_stream
     C, H, W = 1024, 38, 63
@@ -147,17 +168,7 @@ def main():
         time_ms(lambda: ops.unfused_chain(d["key"], flow, d["scale_map"], d["cur"], d["logits"], tmp), 3, 10), pk,
         "algorithmic bytes of the fused op; real traffic is 16F")
     del tmp
-    if not args.quick:
-        E = 2048
-        g = torch.Generator(device=dev).manual_seed(1)
-        Nc = 16
-        ew = torch.randn((Nc, E, H, W), device=dev, generator=g)
-        ec = torch.randn((Nc, E, H, W), device=dev, generator=g)
-        p = ops.PreparedAggregate(d["key"][:Nc], d["mv"][:Nc], flow_kind="raw", cur=d["cur"][:Nc], scale_map=d["scale_map"][:Nc],
-                                  weight_mode="cosine", emb_warp=ew, emb_cur=ec)
-        row("V3 cosine (Fgfa) fp32 NCHW: cosine pre-pass + fused", Nc, 4 * F4 + 40 * HW + 2 * E * HW * 4, time_ms(lambda: p.run(s)), pk,
-            "2 launches")
-        del ew, ec
+    cosine_rows(dev, pk, 16 if args.quick else 64)
 
     # ---- config 3: bf16 NHWC ----
     Nb = 128 if args.quick else 512

@@ -192,6 +192,13 @@ LSFA_API int    lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args);
 LSFA_API int lsfa_cosine_logits(const void* emb_warp, const void* emb_cur, float* logits, int N, int E,
                        int H, int W, int layout, void* stream);
 
+/* Same with a caller scratch (lsfa_cosine_logits_workspace_bytes, 16-byte aligned, no initialisation): NCHW
+ * embeddings then go through the all-TMA pre-pass (whole channel planes by bulk copy, per-CTA partial sums added in
+ * a fixed order: deterministic); without scratch, or when the planes do not fit, this is lsfa_cosine_logits. */
+LSFA_API size_t lsfa_cosine_logits_workspace_bytes(int N, int E, int H, int W, int layout);
+LSFA_API int lsfa_cosine_logits_ws(const void* emb_warp, const void* emb_cur, float* logits, int N, int E, int H, int W,
+                                   int layout, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The reference graph op by op (one kernel per MXNet operator, each a full pass over
  * HBM) - the "unfused" arm of the ablation; same results as the fused op in LOGITS mode
  * with scale_map.  tmp: 5 feature-sized float32 buffers (N*C*H*W each), caller-owned. */

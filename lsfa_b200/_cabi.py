@@ -78,6 +78,8 @@ PROTOTYPES = {
     "lsfa_warp_scale_aggregate_workspace_bytes": (_SZ, [C.POINTER(LsfaAggArgs)]),
     "lsfa_warp_scale_aggregate_num_launches": (_I, [C.POINTER(LsfaAggArgs)]),
     "lsfa_cosine_logits": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "lsfa_cosine_logits_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "lsfa_cosine_logits_ws": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     "lsfa_unfused_chain_f32_nchw": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lsfa_unfused_chain_num_launches": (_I, []),
     "lsfa_blend_logits_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

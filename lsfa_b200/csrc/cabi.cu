@@ -384,6 +384,21 @@ int lsfa_cosine_logits(const void* emb_warp, const void* emb_cur, float* logits,
                      "cosine_logits_nhwc launch");
 }
 
+size_t lsfa_cosine_logits_workspace_bytes(int N, int E, int H, int W, int layout) {
+  if (layout != LSFA_LAYOUT_NCHW_F32 || N <= 0 || E <= 0 || H <= 0 || W <= 0) return 0;
+  return lsfa::cosine_tma_workspace_bytes(N, E, H * W);
+}
+
+int lsfa_cosine_logits_ws(const void* emb_warp, const void* emb_cur, float* logits, int N, int E, int H, int W, int layout,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (layout == LSFA_LAYOUT_NCHW_F32 && emb_warp && emb_cur && logits && N > 0 && E > 0 && H > 0 && W > 0 && workspace) {
+    cudaError_t e = lsfa::launch_cosine_logits_nchw_tma(static_cast<const float*>(emb_warp), static_cast<const float*>(emb_cur),
+                                                        logits, N, E, H * W, workspace, workspace_bytes, as_stream(stream));
+    if (e != cudaErrorNotSupported) return cuda_result(e, "cosine_logits_nchw_tma launch");
+  }
+  return lsfa_cosine_logits(emb_warp, emb_cur, logits, N, E, H, W, layout, stream);
+}
+
 int lsfa_unfused_chain_f32_nchw(const float* key, const float* flow, const float* scale_map, const float* cur,
                                 const float* logits, float* out, float* tmp, int N, int C, int H, int W,
                                 void* stream) {

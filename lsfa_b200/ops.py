@@ -524,16 +524,24 @@ def tile_as(n: int, device) -> torch.Tensor:
     return torch.zeros(n, dtype=torch.int32, device=device)
 
 
-def cosine_logits(emb_warp, emb_cur, layout="nchw") -> torch.Tensor:
-    """compute_weight x2 of Fgfa_net (SYM:111-116,137-139) -> (N,2,H,W) f32."""
+def cosine_logits(emb_warp, emb_cur, layout="nchw", workspace=None) -> torch.Tensor:
+    """compute_weight x2 of Fgfa_net (SYM:111-116,137-139) -> (N,2,H,W) f32.  NCHW embeddings go through the all-TMA
+    pre-pass (scratch allocated here unless given; ``workspace=False`` pins the LDG kernel)."""
     lay = _LAYOUT[layout]
     fdt = _feat_dtype(lay)
     _dev(emb_warp, "emb_warp", fdt)
     _dev(emb_cur, "emb_cur", fdt)
     N, E, H, W = _feature_dims(emb_warp, lay)
     logits = torch.empty((N, 2, H, W), dtype=torch.float32, device=emb_warp.device)
-    A.check(A.load().lsfa_cosine_logits(emb_warp.data_ptr(), emb_cur.data_ptr(), logits.data_ptr(), N, E,
-                                        H, W, lay, _stream()))
+    lib = A.load()
+    if workspace is None:
+        need = lib.lsfa_cosine_logits_workspace_bytes(N, E, H, W, lay)
+        workspace = torch.empty(need, dtype=torch.uint8, device=emb_warp.device) if need else False
+    if workspace is False:
+        A.check(lib.lsfa_cosine_logits(emb_warp.data_ptr(), emb_cur.data_ptr(), logits.data_ptr(), N, E, H, W, lay, _stream()))
+    else:
+        A.check(lib.lsfa_cosine_logits_ws(emb_warp.data_ptr(), emb_cur.data_ptr(), logits.data_ptr(), N, E, H, W, lay,
+                                          workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()))
     return logits
 
 

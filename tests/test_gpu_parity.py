@@ -404,8 +404,13 @@ def test_cosine_logits_op(ops, cuda):
     ec = rng.standard_normal((2, 2048, 9, 7), dtype=np.float32)
     ec[:, :, 0, 0] = 0
     want = np.concatenate([O.cosine_weight(ew, ec), O.cosine_weight(ec, ec)], axis=1)
-    got = host(ops.cosine_logits(dev(ew, cuda), dev(ec, cuda), "nchw"))
+    got = host(ops.cosine_logits(dev(ew, cuda), dev(ec, cuda), "nchw", workspace=False))       # LDG kernel
     assert np.abs(got - want).max() < 2e-6
+    ew2, ec2 = np.ascontiguousarray(ew[:, :, :, :6]), np.ascontiguousarray(ec[:, :, :, :6])    # 9x6: even plane -> all-TMA pre-pass
+    want2 = np.concatenate([O.cosine_weight(ew2, ec2), O.cosine_weight(ec2, ec2)], axis=1)
+    got2 = host(ops.cosine_logits(dev(ew2, cuda), dev(ec2, cuda), "nchw"))
+    assert np.abs(got2 - want2).max() < 2e-6
+    assert np.array_equal(got2, host(ops.cosine_logits(dev(ew2, cuda), dev(ec2, cuda), "nchw")))   # deterministic
     got = host(ops.cosine_logits(ops.to_nhwc(dev(ew, cuda)), ops.to_nhwc(dev(ec, cuda)), "nhwc_f32"))
     assert np.abs(got - want).max() < 2e-6
     assert got[0, 0, 0, 0] == 0.0 and got[0, 1, 0, 0] == 0.0     # eps path: 0/sqrt(1e-10)

@@ -102,7 +102,10 @@ def cosine_rows(dev, pk, Nc):
         time_ms(lambda: p.run(s)), pk, "%d launches" % p.launches)
     lg = torch.empty((Nc, 2, H, W), device=dev)
     row("cosine logits alone (LDG kernel, lsfa_cosine_logits)", Nc, 2 * E * HW * 4 + 8 * HW,
-        time_ms(lambda: ops.cosine_logits(ew, ec)), pk)
+        time_ms(lambda: ops.cosine_logits(ew, ec, workspace=False)), pk, "ablation")
+    wsc = torch.empty(ops.A.load().lsfa_cosine_logits_workspace_bytes(Nc, E, H, W, 0), dtype=torch.uint8, device=dev)
+    row("cosine logits alone (all-TMA pre-pass, lsfa_cosine_logits_ws)", Nc, 2 * E * HW * 4 + 8 * HW,
+        time_ms(lambda: ops.cosine_logits(ew, ec, workspace=wsc)), pk)
 
 
 def main():

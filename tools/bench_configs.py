@@ -88,6 +88,38 @@ def backward_rows(dev, pk, quick):
         time_ms(lambda: ops.warp_backward(d["key"], flow2, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel="gather"), 2, 10), pk)
 
 
+def single_frame_rows(dev, pk):
+    """BASELINE configs[0]: ONE non-key frame (1024x38x63 fp32 + a 600x1000 MV field): latency of the two drop-in
+    operators and of the fused op, eager launches and replayed from a CUDA graph."""
+    C, H, W = 1024, 38, 63
+    HW, F4 = H * W, C * H * W * 4
+    d = synth(1, C, H, W, 600, 1000, dev)
+    s = torch.cuda.current_stream().cuda_stream
+    flow = ops.mv_pool(d["mv"])
+    grid = torch.empty_like(flow)
+    out = torch.empty_like(d["key"])
+    row("cfg1 single frame: mv_pool + GridGenerator + BilinearSampler (3 ops)", 1, 2 * F4 + 32 * HW,
+        time_ms(lambda: ops.BilinearSampler(d["key"], ops.GridGenerator(ops.mv_pool(d["mv"]), out=grid), out=out), 10, 200), pk,
+        "latency, eager")
+    p0 = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw")
+    row("cfg1 single frame: fused warp, raw MV", 1, 2 * F4 + 32 * HW, time_ms(lambda: p0.run(s), 10, 200), pk, "latency, eager")
+    p2 = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                               weight_mode="logits", logits=d["logits"])
+    row("single frame: fused V2", 1, 4 * F4 + 40 * HW, time_ms(lambda: p2.run(s), 10, 200), pk, "latency, eager")
+    for name, p, b in (("cfg1 single frame: fused warp, raw MV", p0, 2 * F4 + 32 * HW), ("single frame: fused V2", p2, 4 * F4 + 40 * HW)):
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                p.run(side.cuda_stream)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(20):
+                    p.run(side.cuda_stream)
+        torch.cuda.synchronize()
+        row(name + " (CUDA graph of 20)", 1, b, time_ms(g.replay, 3, 20) / 20, pk, "latency per frame inside a graph")
+
+
 def cosine_rows(dev, pk, Nc):
     C, H, W, E = 1024, 38, 63, 2048
     HW, F4 = H * W, C * H * W * 4
@@ -113,11 +145,15 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only-backward", action="store_true")
     ap.add_argument("--only-cosine", action="store_true")
+    ap.add_argument("--only-single", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
     if args.only_backward:
         backward_rows(dev, pk, args.quick)
+        return
+    if args.only_single:
+        single_frame_rows(dev, pk)
         return
     if args.only_cosine:
         cosine_rows(dev, pk, 64)
@@ -172,6 +208,7 @@ def main():
         "algorithmic bytes of the fused op; real traffic is 16F")
     del tmp
     cosine_rows(dev, pk, 16 if args.quick else 64)
+    single_frame_rows(dev, pk)
 
     # ---- config 3: bf16 NHWC ----
     Nb = 128 if args.quick else 512

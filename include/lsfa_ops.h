@@ -147,8 +147,8 @@ LSFA_API int lsfa_mv_pool_f32(const float* mv, float* flow, int N, int h, int w,
                      double im_scale, int mode, void* stream);
 
 /* a3+a4+a5 for the residual (image.py:207-222), including the in-place channel aliasing of
- * image.py:217-218.  res: (N,h,w,3); means[3], pixel_scale as config.network.PIXEL_MEANS /
- * PIXEL_SCALE; out (N,3,H,W) float32. */
+ * image.py:217-218.  res: (N,h,w,3); means: HOST pointer to 3 doubles (or NULL = zeros), pixel_scale as
+ * config.network.PIXEL_MEANS / PIXEL_SCALE; out (N,3,H,W) float32. */
 LSFA_API int lsfa_res_pool_i32(const int32_t* res, float* out, int N, int h, int w,
                       const double* means, double pixel_scale, int mode, void* stream);
 LSFA_API int lsfa_res_pool_f32(const float* res, float* out, int N, int h, int w,
@@ -159,6 +159,16 @@ LSFA_API int lsfa_res_pool_f32(const float* res, float* out, int N, int h, int w
  * out (N,oh,ow,2) float32 with oh = cvRound(h*im_scale).  negate=1 applies image.py:54. */
 LSFA_API int lsfa_mv_prepare_i32(const int32_t* mv_coviar, float* mv_out, int N, int h, int w,
                         int oh, int ow, double im_scale, int negate, int hflip, void* stream);
+
+/* a1+a2+a3+a4+a5 for the residual in one pass - replaces lib/utils/image.py:52,59 (the residual of
+ * coviar_py2.load(...,2,True), optional h-flip), :205 (cv2.resize by im_scale, INTER_LINEAR, float32),
+ * :207-215 (pad), :217-218 (aliased colour/mean loop) and :221 (stride-16 reduction).
+ * res_coviar (N,h,w,3) int32 at the video's resolution; oh,ow = cvRound(h*im_scale), cvRound(w*im_scale)
+ * (= h,w when im_scale == 1); means: HOST pointer to 3 doubles or NULL; out (N,3,ceil(oh/16),ceil(ow/16)) f32 =
+ * the `res_diff` input of SYM:575. */
+LSFA_API int lsfa_res_coviar_pool_i32(const int32_t* res_coviar, float* out, int N, int h, int w, int oh, int ow,
+                             double im_scale, int hflip, const double* means, double pixel_scale, int mode,
+                             void* stream);
 
 /* a7 - mx.sym.GridGenerator(data=flow, transform_type='warp') (SYM:306,320,468,571,678).
  * flow, grid: (N,2,H,W) float32. */

@@ -22,6 +22,7 @@ SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu", "
 HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"), os.path.join(CSRC, "aggregate_nchw_plane.cuh"),
            os.path.join(CSRC, "plane_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma.cuh"),
            os.path.join(CSRC, "tma_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma2.cuh"),
+           os.path.join(CSRC, "aggregate_nhwc_tma.cuh"),
            os.path.join(CSRC, "tma2_variant_impl.inc"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "lsfa_ops.h")]
 

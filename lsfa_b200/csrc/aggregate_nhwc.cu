@@ -10,7 +10,10 @@
 // the key feature's reuse is served by the 126 MB L2.  fp32 arithmetic throughout.
 // The cosine-embedding weights (Fgfa_net) are computed in the same pass with warp-shuffle
 // reductions, so this layout needs no workspace and no second kernel.
+#include <cstdlib>
+
 #include "aggregate_nchw_plane.cuh"   // PlaneVariant: the same compile-time variants as the NCHW kernels
+#include "aggregate_nhwc_tma.cuh"     // the all-TMA form (default where it applies)
 
 namespace lsfa {
 
@@ -60,6 +63,10 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
   constexpr int L = V::kLanes;        // channels per 16-byte vector
   constexpr int CSTEP = 32 * L;       // channels per warp pass
   __shared__ TileRec recs[2][kTilePix];
+  // residual conv weights (a10, SYM:66) as (w0,w1,w2,b) per channel, transposed so that the lanes of a warp read
+  // consecutive float4: channel cb + lane*L + k sits at cb + k*32 + lane (cb = multiple of 32*L).  Per-element
+  // global loads of the (C,3) array touched ~24 cache lines per warp instruction: 0.21 of the HBM peak measured.
+  extern __shared__ float4 rnet_s[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const T* __restrict__ key = static_cast<const T*>(P.key);
   const T* __restrict__ scale = static_cast<const T*>(P.scale);
@@ -105,6 +112,16 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
 
   long long tile = blockIdx.x;
   if (tile >= tiles) return;
+  if (HAS_RES && has_res && P.rnet_smem) {
+    const int cpad = (P.C + CSTEP - 1) / CSTEP * CSTEP;
+    for (int j = threadIdx.x; j < cpad; j += blockDim.x) {
+      const int cb = j / CSTEP * CSTEP, k = (j - cb) / 32, ln = j & 31;
+      const int ch = cb + ln * L + k;
+      rnet_s[j] = ch < P.C ? make_float4(__ldg(P.rnet_w + (size_t)ch * 3), __ldg(P.rnet_w + (size_t)ch * 3 + 1),
+                                         __ldg(P.rnet_w + (size_t)ch * 3 + 2), __ldg(P.rnet_b + ch))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   if (warp == kStreamWarps) build_records(tile, recs[0]);
   __syncthreads();
 
@@ -279,10 +296,17 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
                   val = fma2(w11p, f11[i], val);
                   if (has_scale) val = mul2(val, fs[i]);
                   if (HAS_RES && has_res) {
-                    const int ch = c + co + lane * L + 2 * i;
-                    const float* rw = P.rnet_w + (size_t)ch * 3;
-                    const float ra = rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + ch), r0, r1, r2);
-                    const float rb = rnet_term(__ldg(rw + 3), __ldg(rw + 4), __ldg(rw + 5), __ldg(P.rnet_b + ch + 1), r0, r1, r2);
+                    float ra, rb;
+                    if (P.rnet_smem) {
+                      const float4 qa = rnet_s[c + co + (2 * i) * 32 + lane], qb = rnet_s[c + co + (2 * i + 1) * 32 + lane];
+                      ra = rnet_term(qa.x, qa.y, qa.z, qa.w, r0, r1, r2);
+                      rb = rnet_term(qb.x, qb.y, qb.z, qb.w, r0, r1, r2);
+                    } else {
+                      const int ch = c + co + lane * L + 2 * i;
+                      const float* rw = P.rnet_w + (size_t)ch * 3;
+                      ra = rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + ch), r0, r1, r2);
+                      rb = rnet_term(__ldg(rw + 3), __ldg(rw + 4), __ldg(rw + 5), __ldg(P.rnet_b + ch + 1), r0, r1, r2);
+                    }
                     val = fma2(wwp, pair2(ra, rb), val);
                   }
                   o[i] = has_cur ? fma2(wcp, fc[i], val) : val;
@@ -353,7 +377,10 @@ static int nhwc_grid(long long work_groups) {
   return (int)g;
 }
 
-cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st) {
+// kernel: 0 = auto (all-TMA where it applies, else the LDG/STG tile kernel), 1 = LDG/STG tile kernel,
+// 3 = all-TMA or cudaErrorNotSupported
+cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaStream_t st) {
+  AggParams P = P_in;
   const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kTileH - 1) / kTileH;
   const long long tiles = (long long)P.N * tiles_x * tiles_y;
   int dev = 0, sms = 148;
@@ -369,10 +396,39 @@ cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st) {
     else if (has_scale && has_cur && !has_res) var = kVarScaleCur;
     else if (!has_scale && has_cur && has_res) var = kVarResCur;
   }
+  NtPlan Q;
+  const char* env = getenv("LSFA_NHWC_TMA");                    // ablation knob: LSFA_NHWC_TMA=0 keeps the LDG/STG kernel
+  const bool want_tma = kernel == 3 || (kernel == 0 && !(env && env[0] == '0'));
+  if (want_tma && plan_nhwc_tma(P, bf16, var, &Q)) {
+    if (getenv("LSFA_TMA_STATIC")) P.sched = nullptr;
+    if (P.sched) {                                              // one claim counter, zeroed per launch
+      cudaError_t e = cudaMemsetAsync(P.sched, 0, sizeof(unsigned), st);
+      if (e != cudaSuccess) return e;
+    }
+    const long long nb = (long long)P.N * ((P.HW + 31) / 32);
+    const int g = (int)(nb < sms ? nb : sms);                   // persistent: one CTA per SM
+#define LSFA_NT_CASE(V)                                                                         \
+    if (var == V) return bf16 ? launch_nhwc_tma_variant<__nv_bfloat16, V>(P, Q, g, st)          \
+                              : launch_nhwc_tma_variant<float, V>(P, Q, g, st);
+    LSFA_NT_CASE(kVarWarpOnly) LSFA_NT_CASE(kVarScale) LSFA_NT_CASE(kVarScaleCur) LSFA_NT_CASE(kVarResCur)
+#undef LSFA_NT_CASE
+  }
+  if (kernel == 3) return cudaErrorNotSupported;
+  // residual variant: the conv weights go to (dynamic) shared memory when they fit next to a second CTA
+  size_t dsm = 0;
+  P.rnet_smem = 0;
+  if (has_res) {
+    const int cstep = 32 * (bf16 ? 8 : 4);
+    const size_t need = (size_t)((P.C + cstep - 1) / cstep * cstep) * sizeof(float4);
+    if (need <= 40 * 1024 && getenv("LSFA_NHWC_RNET_GLOBAL") == nullptr) {
+      dsm = need;
+      P.rnet_smem = 1;
+    }
+  }
 #define LSFA_NHWC_CASE(V)                                                                              \
   if (var == V) {                                                                                      \
-    if (bf16) agg_nhwc_kernel<__nv_bfloat16, V><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);       \
-    else agg_nhwc_kernel<float, V><<<(unsigned)grid, kNhwcTileThreads, 0, st>>>(P);                    \
+    if (bf16) agg_nhwc_kernel<__nv_bfloat16, V><<<(unsigned)grid, kNhwcTileThreads, dsm, st>>>(P);     \
+    else agg_nhwc_kernel<float, V><<<(unsigned)grid, kNhwcTileThreads, dsm, st>>>(P);                  \
   }
   LSFA_NHWC_CASE(kVarRuntime) LSFA_NHWC_CASE(kVarWarpOnly) LSFA_NHWC_CASE(kVarScale)
   LSFA_NHWC_CASE(kVarScaleCur) LSFA_NHWC_CASE(kVarResCur)

@@ -24,7 +24,7 @@ size_t cosine_tma_workspace_bytes(int N, int E, int HW);
 cudaError_t launch_cosine_logits_nchw_tma(const float* ew, const float* ec, float* logits, int N, int E, int HW,
                                           void* scratch, size_t scratch_bytes, cudaStream_t st);
 // aggregate_nhwc.cu
-cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, cudaStream_t st);
+cudaError_t launch_agg_nhwc(const AggParams& P, bool bf16, int kernel, cudaStream_t st);
 cudaError_t launch_cosine_logits_nhwc(const void* ew, const void* ec, float* logits, int N, int E,
                                       int HW, bool bf16, cudaStream_t st);
 // prep_ops.cu
@@ -32,6 +32,9 @@ cudaError_t launch_mv_pool(const void* mv, bool is_i32, float* flow, int N, int 
                            double scale, int mode, cudaStream_t st);
 cudaError_t launch_res_pool(const void* res, bool is_i32, float* out, int N, int h, int w, int H, int W,
                             const double* means, double pixel_scale, int mode, cudaStream_t st);
+cudaError_t launch_res_coviar_pool(const int* res, float* out, int N, int h, int w, int oh, int ow, int H, int W,
+                                   double im_scale, int hflip, const double* means, double pixel_scale, int mode,
+                                   cudaStream_t st);
 cudaError_t launch_mv_prepare(const int* in, float* out, int N, int h, int w, int oh, int ow,
                               double im_scale, int negate, int hflip, cudaStream_t st);
 cudaError_t launch_grid_generator(const float* flow, float* grid, int N, int H, int W, float half_w,
@@ -184,6 +187,8 @@ size_t records_ws_bytes(const LsfaAggArgs* a) {   // packed sampling records of 
   if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   return (size_t)a->N * a->H * a->W * 32;
 }
+constexpr size_t kNhwcWorkspaceBytes = 64;   // channels-last: one claim counter (padded)
+
 size_t sched_ws_bytes(const LsfaAggArgs* a) {
   if (!a || a->layout != LSFA_LAYOUT_NCHW_F32 || a->N <= 0 || a->H <= 0 || a->W <= 0) return 0;
   const size_t parts = ((size_t)a->H * a->W + 4319) / 4320;      // pixel parts of the all-TMA kernel (9 x 480)
@@ -243,7 +248,18 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
       return cuda_result(lsfa::launch_agg_nchw_plane(P, smem, st), "agg_nchw_plane launch");
     return cuda_result(lsfa::launch_agg_nchw_generic(P, st), "agg_nchw_generic launch");
   }
-  return cuda_result(lsfa::launch_agg_nhwc(P, a->layout == LSFA_LAYOUT_NHWC_BF16, st), "agg_nhwc launch");
+  // channels-last: force_generic 0 = auto (all-TMA kernel where it applies), 1 = LDG/STG tile kernel, 3 = all-TMA or fail.
+  // An optional 64-byte workspace holds the claim counter of the all-TMA kernel (NULL = static batch stride).
+  if (a->force_generic != 0 && a->force_generic != 1 && a->force_generic != 3)
+    return fail(LSFA_E_BADARG, "force_generic %d is not defined for the channels-last layouts (0, 1 or 3)", a->force_generic);
+  if (a->workspace && a->workspace_bytes >= kNhwcWorkspaceBytes && (reinterpret_cast<uintptr_t>(a->workspace) % 4) == 0)
+    P.sched = static_cast<unsigned*>(a->workspace);
+  cudaError_t e = lsfa::launch_agg_nhwc(P, a->layout == LSFA_LAYOUT_NHWC_BF16, a->force_generic, st);
+  if (e == cudaErrorNotSupported) {
+    cudaGetLastError();
+    return fail(LSFA_E_UNSUPPORTED, "the all-TMA channels-last kernel cannot serve these arguments");
+  }
+  return cuda_result(e, "agg_nhwc launch");
 }
 
 }  // namespace
@@ -287,6 +303,20 @@ int lsfa_res_pool_i32(const int32_t* res, float* out, int N, int h, int w, const
 int lsfa_res_pool_f32(const float* res, float* out, int N, int h, int w, const double* means,
                       double pixel_scale, int mode, void* stream) {
   return res_pool_common(res, false, out, N, h, w, means, pixel_scale, mode, stream);
+}
+
+int lsfa_res_coviar_pool_i32(const int32_t* res_coviar, float* out, int N, int h, int w, int oh, int ow, double im_scale,
+                             int hflip, const double* means, double pixel_scale, int mode, void* stream) {
+  if (!res_coviar || !out) return fail(LSFA_E_BADARG, "res_coviar and out are required");
+  if (N <= 0 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  if (mode != LSFA_POOL_CENTRE2X2 && mode != LSFA_POOL_AVG16) return fail(LSFA_E_BADARG, "unknown pool mode %d", mode);
+  if (!(im_scale > 0.0)) return fail(LSFA_E_BADARG, "im_scale must be > 0");
+  const long eh = im_scale == 1.0 ? h : lrint((double)h * im_scale), ew = im_scale == 1.0 ? w : lrint((double)w * im_scale);
+  if (oh != eh || ow != ew)
+    return fail(LSFA_E_SHAPE, "residual %dx%d at im_scale %g resizes to %ldx%ld, but oh,ow = %d,%d", h, w, im_scale, eh, ew, oh, ow);
+  return cuda_result(lsfa::launch_res_coviar_pool(res_coviar, out, N, h, w, oh, ow, ceil16(oh), ceil16(ow), im_scale, hflip,
+                                                  means, pixel_scale, mode, as_stream(stream)),
+                     "res_coviar_pool launch");
 }
 
 int lsfa_mv_prepare_i32(const int32_t* mv_coviar, float* mv_out, int N, int h, int w, int oh, int ow,
@@ -347,6 +377,7 @@ int lsfa_warp_scale_aggregate_bf16_nhwc(const LsfaAggArgs* args, void* stream) {
 }
 
 size_t lsfa_warp_scale_aggregate_workspace_bytes(const LsfaAggArgs* args) {
+  if (args && (args->layout == LSFA_LAYOUT_NHWC_F32 || args->layout == LSFA_LAYOUT_NHWC_BF16)) return kNhwcWorkspaceBytes;
   return (cosine_ws_bytes(args) + 15) / 16 * 16 + cosine_partials_ws_bytes(args) + sched_ws_bytes(args) + records_ws_bytes(args);
 }
 

@@ -62,6 +62,7 @@ struct AggParams {
   long long pool_base;         // all-TMA kernel: items [0,pool_base) are split statically, the rest claimed from sched[0]
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
   int pdl;                     // launched as a programmatic dependent of the record pre-pass
+  int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory
   unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:
                                // [0] = last key row any tap of the part reads + 1, [1] = Hk - first such row; or NULL
 };

@@ -94,6 +94,68 @@ __global__ void mv_prepare_kernel(const int* __restrict__ in, float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------
+// a1+a2+a3+a4+a5 for the residual in ONE pass over coviar's int32 (N,h,w,3) array: h-flip
+// (image.py:59), cv2.resize(fx=fy=im_scale, INTER_LINEAR) on float32 (image.py:205; same routine as the
+// MV's: horizontal pass, vertical pass, no FMA), zero pad to stride 16, the aliased colour/mean loop
+// (image.py:217-218) and the stride-16 reduction (image.py:221).  Only the resized samples the reduction
+// reads are ever computed (4 per cell in parity mode): no (oh,ow,3) float image, no float64 temporaries.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float res_src(const int* __restrict__ img, int w, int y, int x, int ch, int hflip) {
+  const int xs = hflip ? (w - 1 - x) : x;
+  return (float)__ldg(img + ((size_t)y * w + xs) * 3 + ch);
+}
+
+__device__ __forceinline__ double res_resized(const int* __restrict__ img, int h, int w, int oh, int ow, int oy, int ox,
+                                              int ch, double inv_scale, int identity, int hflip) {
+  if (oy >= oh || ox >= ow) return 0.0;                              // the pad of image.py:207-215
+  if (identity) return (double)res_src(img, w, oy, ox, ch, hflip);
+  int sx, sy;
+  float fx, fy;
+  linear_coeff(ox, w, inv_scale, sx, fx);
+  linear_coeff(oy, h, inv_scale, sy, fy);
+  const int sx1 = min(sx + 1, w - 1), sy1 = min(sy + 1, h - 1);
+  const float a0 = __fsub_rn(1.0f, fx), b0 = __fsub_rn(1.0f, fy);
+  const float t0 = __fadd_rn(__fmul_rn(res_src(img, w, sy, sx, ch, hflip), a0), __fmul_rn(res_src(img, w, sy, sx1, ch, hflip), fx));
+  const float t1 = __fadd_rn(__fmul_rn(res_src(img, w, sy1, sx, ch, hflip), a0), __fmul_rn(res_src(img, w, sy1, sx1, ch, hflip), fx));
+  return (double)__fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, fy));
+}
+
+__global__ void res_coviar_pool_kernel(const int* __restrict__ res, float* __restrict__ out, int N, int h, int w, int oh,
+                                       int ow, int H, int W, double inv_scale, int identity, int hflip, ResMeans M,
+                                       int mode) {
+  const long long total = (long long)N * 3 * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % (H * W));
+    const int ch = (int)((i / (H * W)) % 3);
+    const int n = (int)(i / ((long long)3 * H * W));
+    const int y = p / W, x = p - y * W;
+    const int* img = res + (size_t)n * h * w * 3;
+    auto at = [&](int ry, int rx) -> double {                        // padded image after the aliased loop
+      const double c2 = res_resized(img, h, w, oh, ow, ry, rx, 2, inv_scale, identity, hflip);
+      const double n0 = __dmul_rn(__dsub_rn(c2, M.m2), M.s);
+      if (ch == 0) return n0;
+      if (ch == 1) return __dmul_rn(__dsub_rn(res_resized(img, h, w, oh, ow, ry, rx, 1, inv_scale, identity, hflip), M.m1), M.s);
+      return __dmul_rn(__dsub_rn(n0, M.m0), M.s);
+    };
+    double v;
+    if (mode == LSFA_POOL_CENTRE2X2) {
+      const double a = at(16 * y + 7, 16 * x + 7), b = at(16 * y + 7, 16 * x + 8);
+      const double c = at(16 * y + 8, 16 * x + 7), d = at(16 * y + 8, 16 * x + 8);
+      v = __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dadd_rn(c, d)), 0.25);
+    } else {
+      double acc = 0.0;
+#pragma unroll 1
+      for (int r = 0; r < 16; ++r)
+#pragma unroll 1
+        for (int q = 0; q < 16; ++q) acc = __dadd_rn(acc, at(16 * y + r, 16 * x + q));
+      v = __dmul_rn(acc, 1.0 / 256.0);
+    }
+    out[i] = (float)v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // a7: GridGenerator(warp)
 // ---------------------------------------------------------------------------------------
 __global__ void grid_generator_warp_kernel(const float* __restrict__ flow, float* __restrict__ grid,
@@ -299,6 +361,16 @@ cudaError_t launch_res_pool(const void* res, bool is_i32, float* out, int N, int
     res_pool_kernel<int><<<ew_grid(total, 256), 256, 0, st>>>(static_cast<const int*>(res), out, N, h, w, H, W, M, mode);
   else
     res_pool_kernel<float><<<ew_grid(total, 256), 256, 0, st>>>(static_cast<const float*>(res), out, N, h, w, H, W, M, mode);
+  return cudaPeekAtLastError();
+}
+
+cudaError_t launch_res_coviar_pool(const int* res, float* out, int N, int h, int w, int oh, int ow, int H, int W,
+                                   double im_scale, int hflip, const double* means, double pixel_scale, int mode,
+                                   cudaStream_t st) {
+  ResMeans M{means ? means[0] : 0.0, means ? means[1] : 0.0, means ? means[2] : 0.0, pixel_scale};
+  const long long total = (long long)N * 3 * H * W;
+  res_coviar_pool_kernel<<<ew_grid(total, 256), 256, 0, st>>>(res, out, N, h, w, oh, ow, H, W, 1.0 / im_scale,
+                                                              im_scale == 1.0 ? 1 : 0, hflip, M, mode);
   return cudaPeekAtLastError();
 }
 

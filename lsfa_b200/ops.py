@@ -268,6 +268,25 @@ def res_pool(res: torch.Tensor, pixel_means: Sequence[float] = (0.0, 0.0, 0.0),
     return out
 
 
+def res_coviar_pool(res_coviar: torch.Tensor, im_scale: float = 1.0, flipped: bool = False,
+                    pixel_means: Sequence[float] = (0.0, 0.0, 0.0), pixel_scale: float = 1.0,
+                    mode="centre2x2") -> torch.Tensor:
+    """The residual half of get_image + transform_mv_res (image.py:52,59,205,207-222) in one launch:
+    (N,h,w,3) int32 exactly as ``coviar_py2.load(..., 2, True)`` returns it -> (N,3,H,W) float32."""
+    import ctypes
+    _dev(res_coviar, "res_coviar", torch.int32)
+    if res_coviar.dim() != 4 or res_coviar.shape[3] != 3:
+        raise ValueError("res_coviar must be (N,h,w,3), got %s" % (tuple(res_coviar.shape),))
+    N, h, w, _ = res_coviar.shape
+    oh, ow = (h, w) if im_scale == 1.0 else (cv_round(h * im_scale), cv_round(w * im_scale))
+    out = torch.empty((N, 3, _ceil16(oh), _ceil16(ow)), dtype=torch.float32, device=res_coviar.device)
+    means = (ctypes.c_double * 3)(*[float(m) for m in pixel_means])
+    A.check(A.load().lsfa_res_coviar_pool_i32(res_coviar.data_ptr(), out.data_ptr(), N, h, w, oh, ow, float(im_scale),
+                                              int(flipped), ctypes.cast(means, ctypes.c_void_p), float(pixel_scale),
+                                              _POOL[mode], _stream()))
+    return out
+
+
 def transform_mv_res(motion_vector: torch.Tensor, res_diff: torch.Tensor, im_scale: float,
                      pixel_means=(0.0, 0.0, 0.0), pixel_scale: float = 1.0):
     """Device version of lib/utils/image.py:202-228 for inputs already at network scale

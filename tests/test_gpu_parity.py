@@ -95,6 +95,43 @@ def test_mv_prepare_matches_oracle(ops, cuda, h, w, scale, flip):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("h,w,scale", [(90, 160, 0.78125), (72, 96, 1.25), (48, 80, 2.0), (96, 160, 1.0), (75, 131, 1.0),
+                                       (117, 203, 600.0 / 117.0 / 4.0)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_res_coviar_pool_matches_oracle(ops, cuda, h, w, scale, flip):
+    """image.py:52,59,205,207-222 for the residual in one launch, bit-exact against the oracle's whole chain."""
+    rng = np.random.default_rng(5)
+    raw = rng.integers(-64, 65, size=(2, h, w, 3), dtype=np.int32)
+    means, ps = (3.5, -2.25, 10.0), 0.5
+    for mode, om in (("centre2x2", O.POOL_CENTRE2X2), ("avg16", O.POOL_AVG16)):
+        for mm, pp in (((0.0, 0.0, 0.0), 1.0), (means, ps)):
+            got = host(ops.res_coviar_pool(dev(raw, cuda), scale, flipped=flip, pixel_means=mm, pixel_scale=pp, mode=mode))
+            want = np.concatenate([O.to_f32(O.transform_mv_res(np.zeros((h, w, 2), np.float32),
+                                                                r[:, ::-1] if flip else r, scale, mm, pp, om)[1]) for r in raw])
+            assert got.shape == want.shape
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, mm)
+
+
+def test_res_coviar_pool_matches_reference_golden(ops, cuda, golden_ref):
+    """Against the reference's own transform_mv_res outputs: bit-exact where cv2 4.x resizes 3-channel images with
+    the routine the oracle transcribes (scale 1, 2), 2e-5 relative otherwise (see tests/test_oracle_cpu.py)."""
+    g = golden_ref
+    for i in range(int(g["n_cases"])):
+        s = float(g["scale_%d" % i])
+        rin = g["res_in_%d" % i]
+        assert np.array_equal(rin, np.rint(rin)), "fixture residuals are integer-valued"
+        got = host(ops.res_coviar_pool(dev(rin.astype(np.int32)[None], cuda), s))
+        want = g["res_out_%d" % i].astype(np.float32)
+        if s in (1.0, 2.0):
+            assert np.array_equal(got, want), "case %d" % i
+        else:
+            assert np.abs(got - want).max() <= 2e-5 * 64, "case %d" % i
+    rin = g["res_in_m"]
+    got = host(ops.res_coviar_pool(dev(rin.astype(np.int32)[None], cuda), 1.0, pixel_means=tuple(g["means_m"]),
+                                   pixel_scale=float(g["pscale_m"])))
+    assert np.array_equal(got, g["res_out_m"].astype(np.float32))
+
+
 @pytest.mark.parametrize("N,H,W", [(2, 38, 63), (1, 68, 120), (3, 7, 9), (1, 1, 5), (1, 5, 1)])
 def test_grid_generator_bit_exact(ops, cuda, N, H, W):
     rng = np.random.default_rng(11)
@@ -170,7 +207,7 @@ SHAPES = [(3, 64, 38, 63), (2, 8, 68, 120), (4, 16, 7, 9), (2, 32, 37, 63), (1, 
 
 
 def run_fused(ops, cuda, d, mode_name, layout, use_scale=True, use_res=False, flow_kind="raw",
-              force_generic=False, req="write", out=None):
+              force_generic=False, req="write", out=None, workspace=None):
     bf16 = layout == "nhwc_bf16"
     nhwc = layout != "nchw"
 
@@ -203,6 +240,8 @@ def run_fused(ops, cuda, d, mode_name, layout, use_scale=True, use_res=False, fl
         flow = ops.GridGenerator(dev(d["flow"], cuda))
     if out is not None:
         kw["out"] = out
+    if workspace is not None:
+        kw["workspace"] = workspace
     res = ops.warp_scale_aggregate(feat(d["key"]), flow, flow_kind=flow_kind, **kw)
     return ops.to_nchw(res) if nhwc else res
 
@@ -376,6 +415,50 @@ def test_req_add_and_null(ops, cuda):
             sentinel = torch.full_like(first, 7.0)
             run_fused(ops, cuda, d, "logits", layout, req="null", out=sentinel)
             assert float(host(sentinel).min()) == 7.0 == float(host(sentinel).max())
+
+
+@pytest.mark.parametrize("variant", ["warp", "scale", "scale_cur", "mean", "res_cur"])
+@pytest.mark.parametrize("layout", ["nhwc_f32", "nhwc_bf16"])
+@pytest.mark.parametrize("shape", [(5, 64, 38, 63), (2, 1024, 38, 63), (3, 16, 17, 23), (2, 200, 9, 7), (1, 8, 1, 5), (2, 40, 68, 120)])
+def test_nhwc_all_tma_kernel_every_variant(ops, cuda, variant, layout, shape):
+    """force_generic=3 pins the channels-last all-TMA kernel (taps, scale and cur moved by bulk copies, one bulk store
+    per pixel group); it must serve these shapes, agree with the oracle, and agree BIT FOR BIT with the LDG/STG tile
+    kernel (force_generic=1) - same expression chain - with the claim counter (workspace) and without (static stride).
+    Shapes cover partial 32-pixel batches, partial pixel groups, channel runs that are not a multiple of 512 bytes,
+    bypass frames and ragged raw MV images."""
+    N, C, H, W = shape
+    bf16 = layout == "nhwc_bf16"
+    d = make_case(11 + N + C, N, C, H, W, with_res=(variant == "res_cur"), raw="ragged" if H > 1 else True,
+                  with_bypass=(variant in ("scale_cur", "mean", "res_cur") and N >= 3))
+    if bf16:
+        for k in ("key", "cur", "scale_map"):
+            d[k] = O.bf16_round(d[k])
+    call = {"warp": ("none", O.W_NONE, dict(use_scale=False)), "scale": ("none", O.W_NONE, {}),
+            "scale_cur": ("logits", O.W_LOGITS, {}), "mean": ("mean", O.W_MEAN, {}),
+            "res_cur": ("add", O.W_ADD, dict(use_scale=False, use_res=True))}[variant]
+    want = oracle_fused(d, call[1], **call[2])
+    got = host(run_fused(ops, cuda, d, call[0], layout, force_generic=3, **call[2]))
+    if bf16:
+        assert_close_bf16(got, want, what="nhwc tma %s %s" % (variant, shape))
+    else:
+        assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="nhwc tma %s %s" % (variant, shape))
+    ldg = host(run_fused(ops, cuda, d, call[0], layout, force_generic=1, **call[2]))
+    assert np.array_equal(got.view(np.uint32), ldg.view(np.uint32)), "all-TMA and LDG/STG kernels differ"
+    static = host(run_fused(ops, cuda, d, call[0], layout, force_generic=3, workspace=False, **call[2]))
+    assert np.array_equal(got.view(np.uint32), static.view(np.uint32)), "claimed and static batch orders differ"
+
+
+def test_nhwc_all_tma_kernel_full_size_and_shared_key(ops, cuda):
+    """Config-3 shape (1024 x 38 x 63 bf16, raw int32 MVs) with more batches than one wave of CTAs, and the tile_as
+    form (one key feature shared by every frame through key_index)."""
+    d = make_case(77, 6, 1024, 38, 63, with_bypass=True, shared_key=True)
+    for k in ("key", "cur", "scale_map"):
+        d[k] = O.bf16_round(d[k])
+    want = oracle_fused(d, O.W_LOGITS)
+    got = host(run_fused(ops, cuda, d, "logits", "nhwc_bf16", force_generic=3))
+    assert_close_bf16(got, want, what="nhwc tma full size")
+    ldg = host(run_fused(ops, cuda, d, "logits", "nhwc_bf16", force_generic=1))
+    assert np.array_equal(got.view(np.uint32), ldg.view(np.uint32))
 
 
 def test_plane_generic_nhwc_identical_bits(ops, cuda):

@@ -140,12 +140,64 @@ def cosine_rows(dev, pk, Nc):
         time_ms(lambda: ops.cosine_logits(ew, ec, workspace=wsc)), pk)
 
 
+def nhwc_rows(dev, pk, quick, only_tma=False):
+    """Channels-last rows (configs 3 and 4 in bf16, fp32 NHWC, the shipped non-key path and the warp alone in bf16):
+    the all-TMA kernel (default), its static batch stride (no claim counter) and the LDG/STG tile kernel."""
+    s = torch.cuda.current_stream().cuda_stream
+    C, H, W = 1024, 38, 63
+    HW = H * W
+    F4, F2 = C * HW * 4, C * HW * 2
+    kinds = ((0, None, ""), (0, False, ", static batch stride"), (1, None, ", LDG/STG tile kernel"))
+    if only_tma:
+        kinds = (kinds[0], kinds[0], kinds[0])
+    N = 64
+    d = synth(N, C, H, W, 600, 1000, dev)
+    Nb = 128 if quick else 512
+    reps = Nb // N
+    nh = {k: ops.to_nhwc(d[k], torch.bfloat16).repeat(reps, 1, 1, 1) for k in ("key", "cur", "scale_map")}
+    mvb = d["mv"].repeat(reps, 1, 1, 1)
+    lgb = d["logits"].repeat(reps, 1, 1, 1)
+    resb = d["res"].repeat(reps, 1, 1, 1)
+    for fg, ws, nm in kinds:
+        p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
+                                  weight_mode="logits", logits=lgb, layout="nhwc_bf16", force_generic=fg, workspace=ws)
+        row("cfg3 V2 bf16 NHWC batch %d%s" % (Nb, nm), Nb, 4 * F2 + 40 * HW, time_ms(lambda: p.run(s), 3, 10), pk, "ablation" if nm else "")
+    for fg, ws, nm in (kinds[0], kinds[2]):
+        p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], res=resb, rnet_w=d["rnet_w"], rnet_b=d["rnet_b"],
+                                  weight_mode="add", layout="nhwc_bf16", force_generic=fg, workspace=ws)
+        row("V1 shipped non-key path bf16 NHWC batch %d%s" % (Nb, nm), Nb, 3 * F2 + 44 * HW + 16384, time_ms(lambda: p.run(s), 3, 10), pk,
+            "ablation" if nm else "")
+        p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", layout="nhwc_bf16", force_generic=fg, workspace=ws)
+        row("V0 warp only bf16 NHWC batch %d%s" % (Nb, nm), Nb, 2 * F2 + 32 * HW, time_ms(lambda: p.run(s), 3, 10), pk, "ablation" if nm else "")
+    del nh, p, mvb, lgb, resb
+    torch.cuda.empty_cache()
+    nf = {k: ops.to_nhwc(d[k], torch.float32) for k in ("key", "cur", "scale_map")}
+    for fg, ws, nm in kinds:
+        p = ops.PreparedAggregate(nf["key"], d["mv"], flow_kind="raw", cur=nf["cur"], scale_map=nf["scale_map"],
+                                  weight_mode="logits", logits=d["logits"], layout="nhwc_f32", force_generic=fg, workspace=ws)
+        row("V2 fp32 NHWC batch 64%s" % nm, N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk, "ablation" if nm else "")
+    del nf, p, d
+    torch.cuda.empty_cache()
+    H4, W4 = 68, 120
+    N4 = 32 if quick else 128
+    d4 = synth(N4, C, H4, W4, 1080, 1920, dev, max_px=96)
+    nh = {k: ops.to_nhwc(d4[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}
+    for fg, ws, nm in (kinds[0], kinds[2]):
+        p = ops.PreparedAggregate(nh["key"], d4["mv"], flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
+                                  weight_mode="logits", logits=d4["logits"], layout="nhwc_bf16", force_generic=fg, workspace=ws)
+        row("cfg4 V2 bf16 NHWC 68x120 batch %d%s" % (N4, nm), N4, 4 * C * H4 * W4 * 2 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk,
+            "ablation" if nm else "")
+    del d4, nh, p
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only-backward", action="store_true")
     ap.add_argument("--only-cosine", action="store_true")
     ap.add_argument("--only-single", action="store_true")
+    ap.add_argument("--only-nhwc", action="store_true")
+    ap.add_argument("--only-nhwc-tma", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
@@ -154,6 +206,9 @@ def main():
         return
     if args.only_single:
         single_frame_rows(dev, pk)
+        return
+    if args.only_nhwc or args.only_nhwc_tma:
+        nhwc_rows(dev, pk, args.quick, args.only_nhwc_tma)
         return
     if args.only_cosine:
         cosine_rows(dev, pk, 64)
@@ -210,21 +265,9 @@ def main():
     cosine_rows(dev, pk, 16 if args.quick else 64)
     single_frame_rows(dev, pk)
 
-    # ---- config 3: bf16 NHWC ----
-    Nb = 128 if args.quick else 512
-    reps = Nb // N
-    nh = {k: ops.to_nhwc(d[k], torch.bfloat16).repeat(reps, 1, 1, 1) for k in ("key", "cur", "scale_map")}
-    mvb = d["mv"].repeat(reps, 1, 1, 1)
-    lgb = d["logits"].repeat(reps, 1, 1, 1)
-    p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
-                              weight_mode="logits", logits=lgb, layout="nhwc_bf16")
-    row("cfg3 V2 bf16 NHWC batch %d" % Nb, Nb, 4 * F2 + 40 * HW, time_ms(lambda: p.run(s), 3, 10), pk)
-    del nh, p
-    nf = {k: ops.to_nhwc(d[k], torch.float32) for k in ("key", "cur", "scale_map")}
-    p = ops.PreparedAggregate(nf["key"], d["mv"], flow_kind="raw", cur=nf["cur"], scale_map=nf["scale_map"],
-                              weight_mode="logits", logits=d["logits"], layout="nhwc_f32")
-    row("V2 fp32 NHWC batch 64", N, 4 * F4 + 40 * HW, time_ms(lambda: p.run(s)), pk)
-    del nf, p, d, mvb, lgb
+    del d
+    torch.cuda.empty_cache()
+    nhwc_rows(dev, pk, args.quick)
     torch.cuda.empty_cache()
 
     # ---- upstream (8f rank 3): coviar MV accumulation, 64 GOPs x 11 P-frames at 720p ----
@@ -253,11 +296,7 @@ def main():
     p = ops.PreparedAggregate(d4["key"], d4["mv"], flow_kind="raw", cur=d4["cur"], scale_map=d4["scale_map"],
                               weight_mode="logits", logits=d4["logits"])
     row("cfg4 V2 fp32 NCHW 68x120 batch %d" % N4, N4, 4 * C * H4 * W4 * 4 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk)
-    nh = {k: ops.to_nhwc(d4[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}
-    p = ops.PreparedAggregate(nh["key"], d4["mv"], flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
-                              weight_mode="logits", logits=d4["logits"], layout="nhwc_bf16")
-    row("cfg4 V2 bf16 NHWC 68x120 batch %d" % N4, N4, 4 * C * H4 * W4 * 2 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk)
-    del d4, nh, p
+    del d4, p
     torch.cuda.empty_cache()
     backward_rows(dev, pk, args.quick)
 

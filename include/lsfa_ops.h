@@ -121,7 +121,8 @@ typedef struct LsfaAggArgs {
 
   void*   workspace;         /* optional scratch of lsfa_warp_scale_aggregate_workspace_bytes() bytes:
                                 required for NCHW + COSINE (per-pixel logits); otherwise it only enables
-                                dynamic work claiming in the all-TMA kernel (NULL = static split).
+                                dynamic work claiming in the all-TMA kernels (NULL = static split; the
+                                channels-last layouts need 64 bytes: one claim counter).
                                 Contents need no initialisation; one workspace per in-flight call. */
   size_t  workspace_bytes;
 
@@ -131,7 +132,9 @@ typedef struct LsfaAggArgs {
 
   int32_t force_generic;     /* kernel choice (NCHW): 0 auto, 1 generic gather, 2 plane-resident LDG/STG,
                                 3 all-TMA warp-specialised, 4 its experimental 2-CTA-cluster form with a multicast
-                                key load (never chosen automatically); 3 and 4 fail if the kernel cannot serve the args */
+                                key load (never chosen automatically); 3 and 4 fail if the kernel cannot serve the args.
+                                Channels-last layouts: 0 auto (all-TMA gather-by-bulk-copy kernel where it applies),
+                                1 LDG/STG tile kernel, 3 all-TMA or LSFA_E_UNSUPPORTED */
 } LsfaAggArgs;
 
 LSFA_API int         lsfa_version(void);

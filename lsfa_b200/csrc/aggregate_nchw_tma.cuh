@@ -201,6 +201,14 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
     if (!byp) {   // bypass frames: cur already sits in the io buffer, it is stored back as is
       unsigned char* stage_s = ring + (size_t)s * P.stage_bytes;
       const int c0 = chunk * K;
+      // variants without a current feature may skip the shared-memory staging of the output (one STS and one
+      // copy-engine read per element less on the variants that are shared-memory-bandwidth bound)
+      const bool direct = !has_cur && P.direct_store != 0;
+      float* out_g = nullptr;
+      if (direct) {
+        const int part_d = fixed_part >= 0 ? fixed_part : cur_vf - n * P.parts;
+        out_g = static_cast<float*>(P.out) + ((size_t)n * P.C + c0) * P.HW + (size_t)part_d * P.part_pix + tid;
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         float rw0 = 0.f, rw1 = 0.f, rw2 = 0.f, rb = 0.f;
@@ -245,12 +253,15 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
                                             res_s[2 * PPT * kTmaConsumers + q]), v);
               }
               const float o = has_cur ? fmaf(wc[j], cu[g], v) : v;
-              if ((valid >> j) & 1u) io_s[j * kTmaConsumers] = o;
+              if ((valid >> j) & 1u) {
+                if (direct) stg_stream(out_g + (size_t)k * P.HW + j * kTmaConsumers, o);
+                else io_s[j * kTmaConsumers] = o;
+              }
             }
           }
         }
       }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
+      if (!direct) fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA store
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&done[s]);
@@ -421,13 +432,14 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       }
       int s = 0;
       unsigned ph = 0;
+      const bool direct = !has_cur && P.direct_store != 0;   // the consumers wrote the output themselves
       while (live > 0) {
         mbar_wait(&done[s], ph);                       // consumers finished this stage; out is in smem
-        issue_store(s);
+        if (!direct) issue_store(s);
         --live;
         if (!stopped) {
           if (next_item(n, chunk)) {
-            bulk_wait_read_all();                      // the store has drained the stage: safe to refill
+            if (!direct) bulk_wait_read_all();         // the store has drained the stage: safe to refill
             issue_loads(s, n, chunk);
             ++live;
           } else {

@@ -38,6 +38,13 @@ constexpr int kNtGroups = 2;          // consumer groups: group k takes items k,
 constexpr int kNtProducers = LSFA_NT_PRODUCERS;   // producer warps: warp k issues the copies of items k, k + NP, ... (one warp alone
                                                   // needs ~0.9 us of dependent instructions per pixel group: it was the bottleneck)
 constexpr int kNtFirstConsumer = 1 + kNtProducers;
+// Stage s is always filled by the same producer warp and always drained by the same consumer group only if the ring
+// depth is a multiple of both counts.  That is what makes the parity waits safe: a warp that waits for "the previous
+// use of stage s" created that use's predecessor itself, so the barrier is never two phases behind (a parity wait
+// on a barrier two phases behind returns at once).
+constexpr int kNtStageMultiple = (kNtProducers % kNtGroups == 0) ? kNtProducers
+                               : (kNtGroups % kNtProducers == 0) ? kNtGroups : kNtProducers * kNtGroups;
+static_assert(kNtStageMultiple <= 8, "producer / consumer-group counts need too deep a ring");
 constexpr int kNtThreads = (kNtFirstConsumer + kNtGroups * kNtConsumerWarps) * 32;
 constexpr int kNtMaxStages = 8;     // stages actually used: NtPlan::stages (ring budget / stage size)
 constexpr int kNtRecRing = 4;       // record batches in flight ahead of the producer
@@ -85,7 +92,7 @@ struct NtPlan {
   size_t smem;
 };
 
-template <typename T, int VAR>
+template <typename T, int VAR, bool FQ>
 __global__ void __launch_bounds__(kNtThreads, 1)
 agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
   static_assert(VAR != kVarRuntime, "only the compile-time variants");
@@ -157,15 +164,15 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
         const int p = p0 + lane;
         const int y = p / P.W, x = p - y * P.W;
         const PixelLoads ld = issue_pixel_loads(P, n, y, x);
-        const PixelRec t = finish_pixel(P, ld, n, y, x, /*fold=*/true);
-        rec.w00 = t.w00; rec.w01 = t.w01; rec.w10 = t.w10; rec.w11 = t.w11;
-        rec.wc = t.wc; rec.ww = t.ww;
-        rec.i00 = t.i00; rec.i01 = t.i01; rec.i10 = t.i10; rec.i11 = t.i11;
-        if (has_res) {
+        if (has_res) {                                 // issued with the MV taps: one DRAM round trip, not two
           rec.r0 = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
           rec.r1 = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
           rec.r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
         }
+        const PixelRec t = finish_pixel(P, ld, n, y, x, /*fold=*/true);
+        rec.w00 = t.w00; rec.w01 = t.w01; rec.w10 = t.w10; rec.w11 = t.w11;
+        rec.wc = t.wc; rec.ww = t.ww;
+        rec.i00 = t.i00; rec.i01 = t.i01; rec.i10 = t.i10; rec.i11 = t.i11;
       }
       recs[rs * 32 + lane] = rec;
       if (lane == 0) {
@@ -288,22 +295,36 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
   const int cw = (warp - kNtFirstConsumer) % kNtConsumerWarps;
   const int VP = (int)(slot / 16u);                    // 16-byte vectors per pixel
   const int PPX = (VP + 31) / 32;                      // warp passes per pixel
-  // When the passes of a pixel divide the consumer warps, a warp always works on the same 16-byte vector of
-  // every pixel (q fixed): its channels never change, so the residual conv's weights (a10) live in registers.
-  const bool fixed_q = PPX <= kNtConsumerWarps && (kNtConsumerWarps % PPX) == 0;
-  float4 rwq[has_res ? L : 1];
-  if (has_res && fixed_q) {
+  // FQ (residual variant only): the passes of a pixel divide the consumer warps, so a warp always works on the same
+  // 16-byte vector of every pixel: its channels never change and the residual conv's weights (a10) live in
+  // registers, packed as channel pairs for the dual-fp32 instructions.
+  constexpr bool fixed_q = has_res && FQ;
+  constexpr int NW = fixed_q ? L / 2 : 1;
+  f32x2 rw0p[NW], rw1p[NW], rw2p[NW], rbp[NW];
+  if (fixed_q) {
     const int v = (cw % PPX) * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
-      const int ch = v * L + k;
-      rwq[k] = ch < P.C ? make_float4(__ldg(P.rnet_w + (size_t)ch * 3), __ldg(P.rnet_w + (size_t)ch * 3 + 1),
-                                      __ldg(P.rnet_w + (size_t)ch * 3 + 2), __ldg(P.rnet_b + ch))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NW; ++i) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      const int ch = v * L + 2 * i;
+      if (ch + 1 < P.C) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          a[k] = __ldg(P.rnet_w + (size_t)ch * 3 + k);
+          b[k] = __ldg(P.rnet_w + (size_t)(ch + 1) * 3 + k);
+        }
+        a[3] = __ldg(P.rnet_b + ch);
+        b[3] = __ldg(P.rnet_b + ch + 1);
+      }
+      rw0p[i] = pair2(a[0], b[0]);
+      rw1p[i] = pair2(a[1], b[1]);
+      rw2p[i] = pair2(a[2], b[2]);
+      rbp[i] = pair2(a[3], b[3]);
     }
   }
   const int pass0 = cw, pstep = kNtConsumerWarps;      // pass = pixel * PPX + q: q = pass % PPX stays cw % PPX when fixed_q
   T* __restrict__ out = static_cast<T*>(P.out);
+  constexpr int NF = has_res ? 1 : 2;                  // passes in flight (the residual variant holds 4*L weights in registers)
   const int ppx_shift = (PPX & (PPX - 1)) == 0 ? __ffs(PPX) - 1 : -1;   // passes per pixel is normally a power of two
   int s = cgrp % S;
   unsigned ph = (unsigned)(cgrp / S) & 1u;
@@ -316,14 +337,14 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
     T* obase = out + desc[s].out_elem;
     const int passes = np * PPX;
 #pragma unroll 1
-    for (int pass0 = cw; pass0 < passes; pass0 += 2 * kNtConsumerWarps) {
-      // two passes of this warp in flight: all shared-memory reads first, then the arithmetic and the stores
-      uint4 d[2][6];
-      NtPixW w[2];
-      bool on[2];
-      int vv[2], gg[2];
+    for (int pass0 = cw; pass0 < passes; pass0 += NF * kNtConsumerWarps) {
+      // NF passes of this warp in flight: all shared-memory reads first, then the arithmetic and the stores
+      uint4 d[NF][6];
+      NtPixW w[NF];
+      bool on[NF];
+      int vv[NF], gg[NF];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NF; ++h) {
         const int pass = pass0 + h * kNtConsumerWarps;
         const int g = ppx_shift >= 0 ? (pass >> ppx_shift) : pass / PPX;
         const int v = (pass - g * PPX) * 32 + lane;
@@ -348,13 +369,17 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
         }
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NF; ++h) {
         if (!on[h]) continue;
         uint4 res4 = d[h][5];                          // ChooseFeat bypass: the current feature as is
         if (!byp) {
           const f32x2 w00p = pair2(w[h].w00, w[h].w00), w01p = pair2(w[h].w01, w[h].w01), w10p = pair2(w[h].w10, w[h].w10),
                       w11p = pair2(w[h].w11, w[h].w11), wcp = pair2(w[h].wc, w[h].wc), wwp = pair2(w[h].ww, w[h].ww);
           (void)wwp;
+          f32x2 r0p[NF], r1p[NF], r2p[NF];
+          r0p[h] = pair2(w[h].r0, w[h].r0);
+          r1p[h] = pair2(w[h].r1, w[h].r1);
+          r2p[h] = pair2(w[h].r2, w[h].r2);
           constexpr int H2 = L / 2;
           f32x2 f00[H2], f01[H2], f10[H2], f11[H2], fs[H2], fc[H2], o[H2];
           V::unpack2(d[h][0], f00);
@@ -371,18 +396,21 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
             val = fma2(w11p, f11[i], val);
             if (has_scale) val = mul2(val, fs[i]);
             if (has_res) {
-              float ra, rb;
+              f32x2 term;
               if (fixed_q) {
-                const float4 qa = rwq[has_res ? 2 * i : 0], qb = rwq[has_res ? 2 * i + 1 : 0];
-                ra = rnet_term(qa.x, qa.y, qa.z, qa.w, w[h].r0, w[h].r1, w[h].r2);
-                rb = rnet_term(qb.x, qb.y, qb.z, qb.w, w[h].r0, w[h].r1, w[h].r2);
+                // rnet_term() on a channel pair: r = w0*r0; r = fma(w1,r1,r); r = fma(w2,r2,r); r + b  (1*r + b is exact)
+                f32x2 r = mul2(rw0p[fixed_q ? i : 0], r0p[h]);
+                r = fma2(rw1p[fixed_q ? i : 0], r1p[h], r);
+                r = fma2(rw2p[fixed_q ? i : 0], r2p[h], r);
+                term = fma2(pair2(1.0f, 1.0f), r, rbp[fixed_q ? i : 0]);
               } else {
                 const int ch = vv[h] * L + 2 * i;
                 const float* rw = P.rnet_w + (size_t)ch * 3;
-                ra = rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + ch), w[h].r0, w[h].r1, w[h].r2);
-                rb = rnet_term(__ldg(rw + 3), __ldg(rw + 4), __ldg(rw + 5), __ldg(P.rnet_b + ch + 1), w[h].r0, w[h].r1, w[h].r2);
+                const float ra = rnet_term(__ldg(rw), __ldg(rw + 1), __ldg(rw + 2), __ldg(P.rnet_b + ch), w[h].r0, w[h].r1, w[h].r2);
+                const float rb = rnet_term(__ldg(rw + 3), __ldg(rw + 4), __ldg(rw + 5), __ldg(P.rnet_b + ch + 1), w[h].r0, w[h].r1, w[h].r2);
+                term = pair2(ra, rb);
               }
-              val = fma2(wwp, pair2(ra, rb), val);
+              val = fma2(wwp, term, val);
             }
             o[i] = has_cur ? fma2(wcp, fc[i], val) : val;
           }
@@ -427,19 +455,31 @@ inline bool plan_nhwc_tma(const AggParams& P, bool bf16, int var, NtPlan* Q) {
   int stages = (int)(kNtRingBudget / Q->stage_bytes);
   if (stages > kNtMaxStages) stages = kNtMaxStages;
   if (const char* e = getenv("LSFA_NT_STAGES")) stages = max(2, min(stages, atoi(e)));
-  if (stages < kNtGroups) return false;
+  stages -= stages % kNtStageMultiple;
+  if (stages < kNtStageMultiple) return false;
   Q->stages = stages;
   Q->smem = (size_t)kNtOffRing + (size_t)stages * Q->stage_bytes;
   return Q->smem <= 227u * 1024u;
 }
 
-template <typename T, int VAR>
-cudaError_t launch_nhwc_tma_variant(const AggParams& P, const NtPlan& Q, int grid, cudaStream_t st) {
-  auto kfn = agg_nhwc_tma_kernel<T, VAR>;
+template <typename T, int VAR, bool FQ>
+cudaError_t launch_nhwc_tma_fq(const AggParams& P, const NtPlan& Q, int grid, cudaStream_t st) {
+  auto kfn = agg_nhwc_tma_kernel<T, VAR, FQ>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q.smem);
   if (e != cudaSuccess) return e;
   kfn<<<(unsigned)grid, kNtThreads, Q.smem, st>>>(P, Q);
   return cudaPeekAtLastError();
+}
+
+template <typename T, int VAR>
+cudaError_t launch_nhwc_tma_variant(const AggParams& P, const NtPlan& Q, int grid, cudaStream_t st) {
+  if constexpr (VAR == kVarResCur) {
+    const int ppx = ((int)(Q.slot / 16u) + 31) / 32;            // warp passes per pixel
+    const int L = (int)(16 / sizeof(T));
+    if (ppx <= kNtConsumerWarps && kNtConsumerWarps % ppx == 0 && P.C % (2 * L) == 0)
+      return launch_nhwc_tma_fq<T, VAR, true>(P, Q, grid, st);
+  }
+  return launch_nhwc_tma_fq<T, VAR, false>(P, Q, grid, st);
 }
 
 }  // namespace lsfa

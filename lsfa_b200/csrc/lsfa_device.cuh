@@ -63,6 +63,7 @@ struct AggParams {
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
   int pdl;                     // launched as a programmatic dependent of the record pre-pass
   int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory
+  int direct_store;            // all-TMA NCHW kernel, variants without cur: consumers store to global themselves
   unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:
                                // [0] = last key row any tap of the part reads + 1, [1] = Hk - first such row; or NULL
 };

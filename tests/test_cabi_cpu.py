@@ -74,8 +74,13 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.lsfa_warp_scale_aggregate_num_launches(a) == 2
     assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_BADARG            # workspace missing
     a.layout = A.LAYOUT_NHWC_F32
-    assert lib.lsfa_warp_scale_aggregate_workspace_bytes(a) == 0
+    assert lib.lsfa_warp_scale_aggregate_workspace_bytes(a) == 64          # channels-last: one claim counter
     assert lib.lsfa_warp_scale_aggregate_f32_nchw(a, None) == A.E_BADARG   # wrong layout for the suffixed entry
+    a = A.new_args(N=1, C=8, H=4, W=4, layout=A.LAYOUT_NHWC_F32, req=A.REQ_WRITE, key=16, flow=16, out=16, force_generic=2)
+    assert lib.lsfa_warp_scale_aggregate(a, None) == A.E_BADARG            # kernel 2 does not exist for channels-last
+    assert lib.lsfa_res_coviar_pool_i32(None, 16, 1, 32, 32, 32, 32, 1.0, 0, None, 1.0, 0, None) == A.E_BADARG
+    assert lib.lsfa_res_coviar_pool_i32(16, 16, 1, 720, 1280, 562, 999, 0.78125, 0, None, 1.0, 0, None) == A.E_SHAPE
+    assert b"resizes to 562x1000" in lib.lsfa_last_error()
     assert lib.lsfa_mv_pool_i32(None, None, 1, 16, 16, 1.0, 0, None) == A.E_BADARG
     assert lib.lsfa_mv_pool_i32(16, 16, 1, 16, 16, 1.0, 7, None) == A.E_BADARG
     assert lib.lsfa_grid_generator_warp_f32(16, 16, 0, 4, 4, None) == A.E_SHAPE

@@ -461,6 +461,29 @@ def test_nhwc_all_tma_kernel_full_size_and_shared_key(ops, cuda):
     assert np.array_equal(got.view(np.uint32), ldg.view(np.uint32))
 
 
+def test_nhwc_all_tma_kernel_random_shapes_match_tile_kernel(ops, cuda):
+    """Seeded sweep over odd shapes (channel runs from 16 B to 8 KB, planes from 1 to ~700 pixels, 1-7 frames): the
+    all-TMA channels-last kernel and the LDG/STG tile kernel must agree bit for bit, three launches each (a hand-shake
+    error between record warp, producers and consumer groups shows up as a hang or as a wrong pixel group)."""
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        bf16 = bool(it & 1)
+        lanes = 8 if bf16 else 4
+        C = int(rng.choice([lanes, 2 * lanes, 24, 40, 72, 136, 256, 520, 1024, 2048]))
+        C = (C + lanes - 1) // lanes * lanes
+        H, W = int(rng.integers(1, 27)), int(rng.integers(1, 27))
+        N = int(rng.integers(1, 8))
+        variant = ["warp", "scale", "scale_cur", "res_cur"][it % 4]
+        layout = "nhwc_bf16" if bf16 else "nhwc_f32"
+        d = make_case(300 + it, N, C, H, W, with_res=(variant == "res_cur"), with_bypass=(variant in ("scale_cur", "res_cur") and N >= 3))
+        call = {"warp": ("none", dict(use_scale=False)), "scale": ("none", {}), "scale_cur": ("logits", {}),
+                "res_cur": ("add", dict(use_scale=False, use_res=True))}[variant]
+        ref = host(run_fused(ops, cuda, d, call[0], layout, force_generic=1, **call[1]))
+        for rep in range(3):
+            got = host(run_fused(ops, cuda, d, call[0], layout, force_generic=3, workspace=False if rep == 2 else None, **call[1]))
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (it, N, C, H, W, variant, layout, rep)
+
+
 def test_plane_generic_nhwc_identical_bits(ops, cuda):
     """The three f32 kernels evaluate the same fmaf chain: results must agree bit for bit."""
     d = make_case(33, 3, 64, 38, 63, with_bypass=True)

@@ -190,6 +190,26 @@ def nhwc_rows(dev, pk, quick, only_tma=False):
     del d4, nh, p
 
 
+def nocur_rows(dev, pk):
+    """The NCHW variants without a current feature (the two drop-in operators, the fused warp, warp x scale)."""
+    s = torch.cuda.current_stream().cuda_stream
+    C, H, W, N = 1024, 38, 63, 64
+    HW, F4 = H * W, C * H * W * 4
+    d = synth(N, C, H, W, 600, 1000, dev)
+    flow = ops.mv_pool(d["mv"])
+    grid = ops.GridGenerator(flow)
+    out = torch.empty_like(d["key"])
+    row("cfg1 V0 GridGenerator+BilinearSampler (2 ops, fp32 NCHW)", N, 2 * F4 + 8 * HW,
+        time_ms(lambda: ops.BilinearSampler(d["key"], ops.GridGenerator(flow, out=grid), out=out)), pk, "drop-in operators")
+    p = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw")
+    row("cfg1 V0 fused warp only, raw MV pooled in-kernel", N, 2 * F4 + 32 * HW, time_ms(lambda: p.run(s)), pk)
+    p = ops.PreparedAggregate(d["key"], flow, flow_kind="flow", scale_map=d["scale_map"])
+    row("batch path: warp x scale (SYM:678-680), flow given", N, 3 * F4 + 8 * HW, time_ms(lambda: p.run(s)), pk)
+    d4 = synth(32, C, 68, 120, 1080, 1920, dev, max_px=96)
+    p = ops.PreparedAggregate(d4["key"], d4["mv"], flow_kind="raw")
+    row("V0 fused warp only 68x120 batch 32", 32, 2 * C * 68 * 120 * 4 + 32 * 68 * 120, time_ms(lambda: p.run(s), 3, 10), pk)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -198,6 +218,7 @@ def main():
     ap.add_argument("--only-single", action="store_true")
     ap.add_argument("--only-nhwc", action="store_true")
     ap.add_argument("--only-nhwc-tma", action="store_true")
+    ap.add_argument("--only-nocur", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
@@ -206,6 +227,9 @@ def main():
         return
     if args.only_single:
         single_frame_rows(dev, pk)
+        return
+    if args.only_nocur:
+        nocur_rows(dev, pk)
         return
     if args.only_nhwc or args.only_nhwc_tma:
         nhwc_rows(dev, pk, args.quick, args.only_nhwc_tma)

@@ -16,3 +16,7 @@ done
 echo "== default quick"; timeout 600 python tools/bench_configs.py --only-nhwc-tma --quick 2>/dev/null | sort -u > gpurun_out/nhwc_${TAG}_k.jsonl; show gpurun_out/nhwc_${TAG}_k.jsonl
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:agg_nhwc_tma -c 1 -f -o gpurun_out/prof_nhwc_tma_$TAG \
     python tools/bench_configs.py --only-nhwc-tma --quick > gpurun_out/ncu_nhwc_tma_$TAG.log 2>&1; echo "ncu rc=$?"
+echo "== NCHW variants without cur: staged TMA store (default)"; timeout 300 python tools/bench_configs.py --only-nocur 2>/dev/null > gpurun_out/nocur_${TAG}_a.jsonl; show gpurun_out/nocur_${TAG}_a.jsonl
+echo "== NCHW variants without cur: LSFA_TMA_DIRECT_STORE=1"; LSFA_TMA_DIRECT_STORE=1 timeout 300 python tools/bench_configs.py --only-nocur 2>/dev/null > gpurun_out/nocur_${TAG}_b.jsonl; show gpurun_out/nocur_${TAG}_b.jsonl
+LSFA_TMA_DIRECT_STORE=1 timeout 600 python -m pytest tests -m gpu -x -q -k "all_tma_kernel_every_variant or bilinear_sampler or identical_bits or row_trimmed" 2>&1 | tail -2
+echo "== full suite"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

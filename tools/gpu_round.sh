@@ -13,6 +13,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --c
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:agg_nchw_tma -s 3 -c 2 -f -o gpurun_out/prof_tma_$TAG \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 1 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:agg_nhwc_kernel -c 2 -f -o gpurun_out/prof_nhwc_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:agg_nhwc_tma -c 2 -f -o gpurun_out/prof_nhwc_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full_nhwc_$TAG.log 2>&1; echo "ncu nhwc rc=$?"
 ls -la gpurun_out/

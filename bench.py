@@ -324,7 +324,8 @@ def run_ours(args):
     bi, bo = agg.bytes_per_call()
     e2e = {"value": e2e_frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "launches_per_step": agg.launches // max(1, e2e_steps),
-           "api": "lsfa_b200.host.HostAggregator (pinned host in/out, %d-frame chunks, 3-stream pipeline)" % agg.chunk}
+           "api": "lsfa_b200.host.HostAggregator (pinned host in/out, %d-frame chunks, 3-stream pipeline; of each "
+                  "600x1000 MV field only the 2 rows in 16 the reference's stride-16 resize reads cross PCIe)" % agg.chunk}
     checksum = float(out_host[0, 0, 0, :8].sum())    # the result really is on the host
 
     extra = {}

@@ -173,6 +173,15 @@ LSFA_API int lsfa_res_coviar_pool_i32(const int32_t* res_coviar, float* out, int
                              double im_scale, int hflip, const double* means, double pixel_scale, int mode,
                              void* stream);
 
+/* Host-side helper of the reference-facing host path (lsfa_b200.host.HostAggregator; the reference copies every
+ * batch host -> device in core/DataParallelExecutorGroup.py:24-39): enqueue the host -> device copy of ONLY the MV rows
+ * the parity-mode reduction reads - rows 16k+7 and 16k+8 of each (h,w,2) image (lib/utils/image.py:221 as
+ * LSFA_POOL_CENTRE2X2) - into the same positions of a full-size device image: 1/8 of the bytes.  mv_host: pinned host
+ * memory, (N,h,w,2) 4-byte elements; mv_dev: device image of the same shape (rows never copied are never read by the
+ * LSFA_FLOW_RAW_* / LSFA_POOL_CENTRE2X2 kernels).  Returns the number of bytes enqueued through *bytes_out (optional). */
+LSFA_API int lsfa_mv_centre_rows_h2d(const void* mv_host, void* mv_dev, int N, int h, int w, size_t* bytes_out,
+                            void* stream);
+
 /* a7 - mx.sym.GridGenerator(data=flow, transform_type='warp') (SYM:306,320,468,571,678).
  * flow, grid: (N,2,H,W) float32. */
 LSFA_API int lsfa_grid_generator_warp_f32(const float* flow, float* grid, int N, int H, int W,

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "lsfa_res_pool_i32": (_I, [_P, _P, _I, _I, _I, _P, _D, _I, _P]),
     "lsfa_res_pool_f32": (_I, [_P, _P, _I, _I, _I, _P, _D, _I, _P]),
     "lsfa_res_coviar_pool_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _D, _I, _P, _D, _I, _P]),
+    "lsfa_mv_centre_rows_h2d": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "lsfa_mv_prepare_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _D, _I, _I, _P]),
     "lsfa_grid_generator_warp_f32": (_I, [_P, _P, _I, _I, _I, _P]),
     "lsfa_bilinear_sampler_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -398,7 +398,13 @@ cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaSt
   }
   NtPlan Q;
   const char* env = getenv("LSFA_NHWC_TMA");                    // ablation knob: LSFA_NHWC_TMA=0 keeps the LDG/STG kernel
-  const bool want_tma = kernel == 3 || (kernel == 0 && !(env && env[0] == '0'));
+  bool want_tma = kernel == 3 || (kernel == 0 && !(env && env[0] == '0'));
+  // bf16 blend variants on small batches: the two kernels are within 1-2 % at large batch, and the all-TMA kernel
+  // pays ~12 us of ramp-up and tail per launch (measured: 64 frames of 1024x38x63 bf16 0.887 vs 0.919 of the peak for
+  // the tile kernel; 512 frames 0.939 vs 0.929).  Below ~64 record batches per SM the tile kernel is chosen.
+  if (kernel == 0 && bf16 && (var == kVarScaleCur || var == kVarScale) &&
+      (long long)P.N * ((P.HW + 31) / 32) < 64LL * sms)
+    want_tma = false;
   if (want_tma && plan_nhwc_tma(P, bf16, var, &Q)) {
     if (getenv("LSFA_TMA_STATIC")) P.sched = nullptr;
     if (P.sched) {                                              // one claim counter, zeroed per launch

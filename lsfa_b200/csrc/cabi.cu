@@ -319,6 +319,33 @@ int lsfa_res_coviar_pool_i32(const int32_t* res_coviar, float* out, int N, int h
                      "res_coviar_pool launch");
 }
 
+int lsfa_mv_centre_rows_h2d(const void* mv_host, void* mv_dev, int N, int h, int w, size_t* bytes_out, void* stream) {
+  if (!mv_host || !mv_dev) return fail(LSFA_E_BADARG, "mv_host and mv_dev are required");
+  if (N <= 0 || h <= 0 || w <= 0) return fail(LSFA_E_SHAPE, "non-positive dims N=%d h=%d w=%d", N, h, w);
+  const size_t row = (size_t)w * 8, frame = row * (size_t)h, pitch = 16 * row;
+  const int pairs = (h - 7) / 16 + ((h - 7) % 16 >= 2 ? 1 : 0);     // blocks whose rows 16k+7 AND 16k+8 both exist
+  const bool lone = h >= 8 && (h - 8) % 16 == 0;                      // a last block with row 16k+7 only
+  size_t bytes = 0;
+  cudaStream_t st = as_stream(stream);
+  for (int n = 0; n < N; ++n) {
+    const char* src = static_cast<const char*>(mv_host) + (size_t)n * frame + 7 * row;
+    char* dst = static_cast<char*>(mv_dev) + (size_t)n * frame + 7 * row;
+    if (pairs > 0) {
+      cudaError_t e = cudaMemcpy2DAsync(dst, pitch, src, pitch, 2 * row, (size_t)pairs, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return cuda_result(e, "mv_centre_rows_h2d");
+      bytes += 2 * row * (size_t)pairs;
+    }
+    if (lone) {
+      const size_t off = (size_t)(h - 1 - 7) * row;
+      cudaError_t e = cudaMemcpyAsync(dst + off, src + off, row, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return cuda_result(e, "mv_centre_rows_h2d");
+      bytes += row;
+    }
+  }
+  if (bytes_out) *bytes_out = bytes;
+  return LSFA_OK;
+}
+
 int lsfa_mv_prepare_i32(const int32_t* mv_coviar, float* mv_out, int N, int h, int w, int oh, int ow,
                         double im_scale, int negate, int hflip, void* stream) {
   if (!mv_coviar || !mv_out) return fail(LSFA_E_BADARG, "mv_coviar and mv_out are required");

@@ -681,6 +681,48 @@ def test_host_aggregator_pipeline(ops, cuda):
                      scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="host pipeline")
 
 
+@pytest.mark.parametrize("h", [600, 608, 599, 24, 23, 9, 8, 7, 3])
+def test_mv_centre_rows_h2d_copies_exactly_what_the_reduction_reads(ops, cuda, h):
+    """lsfa_mv_centre_rows_h2d moves rows 16k+7 and 16k+8 (those below h) and nothing else; pooling the partial device
+    image gives the bits of pooling the whole field."""
+    import ctypes
+    from lsfa_b200 import _cabi as A
+    w, N = 50, 3
+    rng = np.random.default_rng(h)
+    mv = rng.integers(-64, 65, size=(N, h, w, 2), dtype=np.int32)
+    hmv = torch.from_numpy(mv).pin_memory()
+    dmv = torch.full((N, h, w, 2), 12345, dtype=torch.int32, device=cuda)
+    nbytes = ctypes.c_size_t(0)
+    A.check(A.load().lsfa_mv_centre_rows_h2d(hmv.data_ptr(), dmv.data_ptr(), N, h, w, ctypes.cast(ctypes.byref(nbytes), ctypes.c_void_p),
+                                             torch.cuda.current_stream().cuda_stream))
+    got = host(dmv).astype(np.int32)
+    rows = [r for r in range(h) if r % 16 in (7, 8)]
+    assert nbytes.value == N * len(rows) * w * 8
+    want = np.full_like(mv, 12345)
+    want[:, rows] = mv[:, rows]
+    assert np.array_equal(got, want)
+    if rows:
+        a = host(ops.mv_pool(dmv))
+        b = host(ops.mv_pool(dev(mv, cuda)))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_host_aggregator_ragged_mv(ops, cuda):
+    """Host pipeline with an MV field whose height is not a multiple of 16 (the last block keeps row 16k+7 only)."""
+    from lsfa_b200.host import HostAggregator
+    N, C, H, W = 3, 16, 12, 9
+    d = make_case(56, N, C, H, W, raw="ragged")
+    host_in = {k: torch.from_numpy(d[k]).pin_memory() for k in ("key", "cur", "scale_map", "mv", "logits")}
+    out_host = torch.empty((N, C, H, W), dtype=torch.float32).pin_memory()
+    agg = HostAggregator(N, C, H, W, d["mv"].shape[1:3], cuda, chunk=2, depth=2)
+    agg(host_in, out_host)
+    agg.synchronize()
+    assert_close_f32(out_host.numpy(), oracle_fused(d, O.W_LOGITS),
+                     scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="host pipeline, ragged mv")
+    bi, _ = agg.bytes_per_call()
+    assert bi == N * (3 * C * H * W * 4 + agg.mv_rows_copied() * d["mv"].shape[2] * 8 + 2 * H * W * 4)
+
+
 def test_exact_two_phase_key_frame_graphs(ops, cuda):
     """get_key_test_symbol end to end (SYM:468-477): K1 warp x scale (lsfa) -> embedding / Nq convolutions
     (library GEMMs: cuDNN) -> K2 cosine + softmax blend (lsfa), against the oracle with NumPy convolutions."""

@@ -21,18 +21,30 @@ struct MvRec {  // one AVMotionVector, the six fields the reference reads
   int w, h, src_x, src_y, dst_x, dst_y;
 };
 
-__global__ void mvacc_init_kernel(int2* __restrict__ accu, int* __restrict__ owner, int N, int height, int width) {
-  const long long total = (long long)N * height * width;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i % ((long long)height * width));
-    accu[i] = make_int2(p % width, p / width);     // coviar_data_loader.c:322-326
-    owner[i] = 0;
-  }
+// The accumulated field holds pixel coordinates: 16 bits per component are enough for frames up to 32767 x 32767
+// (A = short2: half the bytes of the reference's int pairs through HBM); larger frames use A = int2.
+template <typename A>
+__device__ __forceinline__ A make_xy(int x, int y);
+template <>
+__device__ __forceinline__ int2 make_xy<int2>(int x, int y) { return make_int2(x, y); }
+template <>
+__device__ __forceinline__ short2 make_xy<short2>(int x, int y) { return make_short2((short)x, (short)y); }
+
+// The per-pixel kernels run on a (width/256, height, N) grid: x, y and the GOP come from the block and thread indices
+// (a flat 64-bit index cost a 64-bit division and two 32-bit ones per pixel, which made the gather instruction bound).
+template <typename A>
+__global__ void mvacc_init_kernel(A* __restrict__ accu, int* __restrict__ owner, int height, int width) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= width) return;
+  const size_t i = ((size_t)blockIdx.z * height + y) * width + x;
+  accu[i] = make_xy<A>(x, y);     // coviar_data_loader.c:322-326
+  owner[i] = 0;
 }
 
-// (A) owner[dst] = max over covering vectors of (list index + 1)
+// tag = (t+1) << 24 when the owner map is never cleared (a later frame's entries are larger than any stale one: one
+// write and one pass over the map less per P-frame), 0 when the gather clears it (T > 126 or M >= 2^24 vectors)
 __global__ void mvacc_owner_kernel(const MvRec* __restrict__ mvs, const int* __restrict__ counts, int* __restrict__ owner,
-                                   int t, int T, int M, int height, int width, int max_block) {
+                                   int t, int T, int M, int height, int width, int tag) {
   const int n = blockIdx.z;
   const int cnt = min(__ldg(counts + (size_t)n * T + t), M);
   const int i = blockIdx.y * blockDim.y + threadIdx.y;          // vector index
@@ -44,42 +56,77 @@ __global__ void mvacc_owner_kernel(const MvRec* __restrict__ mvs, const int* __r
   if (bw <= 0 || bh <= 0) return;
   int* own = owner + (size_t)n * height * width;
   for (int q = threadIdx.x; q < bw * bh; q += blockDim.x) {
-    const int xs = x_lo + q / bh, ys = y_lo + q % bh;           // x outer, y inner like the reference (order is irrelevant here)
+    const int ys = y_lo + q / bw, xs = x_lo + q % bw;           // lanes run along x: 16 neighbouring pixels per 64-byte segment
+                                                                // (the reference walks x outer, y inner; the order is irrelevant here)
     const int dx = mv.dst_x + xs, dy = mv.dst_y + ys, sx = mv.src_x + xs, sy = mv.src_y + ys;
     if (dy >= 0 && dy < height && dx >= 0 && dx < width && sy >= 0 && sy < height && sx >= 0 && sx < width)
-      atomicMax(own + (size_t)dy * width + dx, i + 1);
+      atomicMax(own + (size_t)dy * width + dx, tag + i + 1);
   }
-  (void)max_block;
 }
 
-// (B) gather + clear owner
-__global__ void mvacc_gather_kernel(const MvRec* __restrict__ mvs, const int2* __restrict__ accu_old, int2* __restrict__ accu_new,
-                                    int* __restrict__ owner, int t, int T, int M, int N, int height, int width) {
-  const long long hw = (long long)height * width, total = (long long)N * hw;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i / hw);
-    const int p = (int)(i - (long long)n * hw);
-    const int o = owner[i];
-    int2 v = accu_old[i];
-    if (o > 0) {
-      const MvRec mv = mvs[((size_t)n * T + t) * M + (o - 1)];
-      const int x = p % width, y = p / width;
-      const int sx = mv.src_x + (x - mv.dst_x), sy = mv.src_y + (y - mv.dst_y);
-      v = accu_old[(size_t)n * hw + (size_t)sy * width + sx];
-      owner[i] = 0;
+// (B) gather (+ clear owner when the entries are not tagged).  Every pixel is a chain of three dependent loads
+// (owner -> that vector's src/dst -> accu_old at the source pixel) and the kernel is latency bound (one pixel per
+// thread: 2.5 TB/s of traffic at full occupancy), so a thread walks kGatherRows rows of its column at once, each round
+// of loads issued for all of them before any is used (measured per P-frame, 64 GOPs at 720p: 1 row 303 us, 4 rows
+// 182 us, 8 rows 229 us).
+#ifndef LSFA_GATHER_ROWS
+#define LSFA_GATHER_ROWS 4
+#endif
+constexpr int kGatherRows = LSFA_GATHER_ROWS;
+
+template <typename A>
+__global__ void __launch_bounds__(256)
+mvacc_gather_kernel(const MvRec* __restrict__ mvs, const A* __restrict__ accu_old, A* __restrict__ accu_new,
+                    int* __restrict__ owner, int t, int T, int M, int height, int width, int tag) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kGatherRows, n = blockIdx.z;
+  if (x >= width) return;
+  const size_t frame = (size_t)n * height * width;
+  const MvRec* list = mvs + ((size_t)n * T + t) * M;
+  int o[kGatherRows];
+  A v[kGatherRows];
+#pragma unroll
+  for (int u = 0; u < kGatherRows; ++u) {                // round 1: owner + own value
+    o[u] = 0;
+    if (y0 + u < height) {
+      const size_t i = frame + (size_t)(y0 + u) * width + x;
+      o[u] = owner[i];
+      v[u] = accu_old[i];
     }
-    accu_new[i] = v;
   }
+  int2 ms[kGatherRows], md[kGatherRows];
+#pragma unroll
+  for (int u = 0; u < kGatherRows; ++u) {                // round 2: the owning vector's src and dst
+    if (tag) o[u] = (o[u] >> 24) == (tag >> 24) ? (o[u] & 0xffffff) : 0;       // entries of earlier frames are stale
+    ms[u] = md[u] = make_int2(0, 0);
+    if (o[u] > 0) {
+      const int2* rec = reinterpret_cast<const int2*>(list + (o[u] - 1));
+      ms[u] = __ldg(rec + 1);                            // (src_x, src_y)
+      md[u] = __ldg(rec + 2);                            // (dst_x, dst_y)
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kGatherRows; ++u)                  // round 3: the gather proper
+    if (o[u] > 0) {
+      const int sx = ms[u].x + (x - md[u].x), sy = ms[u].y + (y0 + u - md[u].y);
+      v[u] = accu_old[frame + (size_t)sy * width + sx];
+    }
+#pragma unroll
+  for (int u = 0; u < kGatherRows; ++u)
+    if (y0 + u < height) {
+      const size_t i = frame + (size_t)(y0 + u) * width + x;
+      accu_new[i] = v[u];
+      if (!tag && o[u] > 0) owner[i] = 0;
+    }
 }
 
 // target frame: mv = (x,y) - accu   (:130-139), layout (N,height,width,2) like the numpy array coviar returns
-__global__ void mvacc_finish_kernel(const int2* __restrict__ accu, int2* __restrict__ mv_out, int N, int height, int width) {
-  const long long total = (long long)N * height * width;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i % ((long long)height * width));
-    const int2 a = accu[i];
-    mv_out[i] = make_int2(p % width - a.x, p / width - a.y);
-  }
+template <typename A>
+__global__ void mvacc_finish_kernel(const A* __restrict__ accu, int2* __restrict__ mv_out, int height, int width) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= width) return;
+  const size_t i = ((size_t)blockIdx.z * height + y) * width + x;
+  const A a = accu[i];
+  mv_out[i] = make_int2(x - (int)a.x, y - (int)a.y);
 }
 
 // residual (:141-175, accumulate case): res[y][x][c] = cur[y][x][c] - iframe[src_y][src_x][c], src = (x,y) - mv
@@ -104,23 +151,34 @@ static inline int ew_grid2(long long total, int threads) {
   return (int)g;
 }
 
+template <typename A>
+static cudaError_t run_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
+                                     int* mv_out, void* workspace, cudaStream_t st) {
+  const long long hw = (long long)height * width;
+  A* accu0 = static_cast<A*>(workspace);
+  A* accu1 = accu0 + (size_t)N * hw;
+  int* owner = reinterpret_cast<int*>(accu1 + (size_t)N * hw);
+  const dim3 pg((width + 255) / 256, height, N);         // one thread per pixel: (x block, y, GOP)
+  const dim3 gg((width + 255) / 256, (height + kGatherRows - 1) / kGatherRows, N);
+  const bool tagged = T <= 126 && M < (1 << 24);
+  mvacc_init_kernel<A><<<pg, 256, 0, st>>>(accu0, owner, height, width);
+  A *old_b = accu0, *new_b = accu1;
+  for (int t = 0; t < T; ++t) {
+    const int tag = tagged ? (t + 1) << 24 : 0;
+    dim3 blk(32, 8), grid(1, (M + 7) / 8, N);
+    mvacc_owner_kernel<<<grid, blk, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), counts, owner, t, T, M, height, width, tag);
+    mvacc_gather_kernel<A><<<gg, 256, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), old_b, new_b, owner, t, T, M, height, width, tag);
+    A* tmp = old_b; old_b = new_b; new_b = tmp;       // :126 memcpy(accu_src_old, accu_src)
+  }
+  mvacc_finish_kernel<A><<<pg, 256, 0, st>>>(old_b, reinterpret_cast<int2*>(mv_out), height, width);
+  return cudaPeekAtLastError();
+}
+
 cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
                                  int* mv_out, void* workspace, cudaStream_t st) {
-  const long long hw = (long long)height * width;
-  int2* accu0 = static_cast<int2*>(workspace);
-  int2* accu1 = accu0 + (size_t)N * hw;
-  int* owner = reinterpret_cast<int*>(accu1 + (size_t)N * hw);
-  const int g = ew_grid2((long long)N * hw, 256);
-  mvacc_init_kernel<<<g, 256, 0, st>>>(accu0, owner, N, height, width);
-  int2 *old_b = accu0, *new_b = accu1;
-  for (int t = 0; t < T; ++t) {
-    dim3 blk(32, 8), grid(1, (M + 7) / 8, N);
-    mvacc_owner_kernel<<<grid, blk, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), counts, owner, t, T, M, height, width, 0);
-    mvacc_gather_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), old_b, new_b, owner, t, T, M, N, height, width);
-    int2* tmp = old_b; old_b = new_b; new_b = tmp;       // :126 memcpy(accu_src_old, accu_src)
-  }
-  mvacc_finish_kernel<<<g, 256, 0, st>>>(old_b, reinterpret_cast<int2*>(mv_out), N, height, width);
-  return cudaPeekAtLastError();
+  if (height <= 32767 && width <= 32767)
+    return run_mv_accumulate<short2>(mvs, counts, N, T, M, height, width, mv_out, workspace, st);
+  return run_mv_accumulate<int2>(mvs, counts, N, T, M, height, width, mv_out, workspace, st);
 }
 
 cudaError_t launch_coviar_residual(const unsigned char* iframe, const unsigned char* cur, const int* mv, int* res, int N,

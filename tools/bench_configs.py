@@ -210,6 +210,28 @@ def nocur_rows(dev, pk):
     row("V0 fused warp only 68x120 batch 32", 32, 2 * C * 68 * 120 * 4 + 32 * 68 * 120, time_ms(lambda: p.run(s), 3, 10), pk)
 
 
+def upstream_rows(dev, pk, quick):
+    """Upstream (8f rank 3): coviar MV accumulation, 64 GOPs x 11 P-frames at 720p."""
+    Na, T, ha, wa = (16 if quick else 64), 11, 720, 1280
+    bx, by = wa // 16, ha // 16
+    M = bx * by
+    g = torch.Generator(device=dev).manual_seed(3)
+    cx = (torch.arange(bx, device=dev, dtype=torch.int32) * 16 + 8).view(1, 1, 1, bx).expand(Na, T, by, bx)
+    cy = (torch.arange(by, device=dev, dtype=torch.int32) * 16 + 8).view(1, 1, by, 1).expand(Na, T, by, bx)
+    off = torch.randint(-16, 17, (Na, T, by, bx, 2), device=dev, generator=g, dtype=torch.int32)
+    off[torch.rand((Na, T, by, bx), device=dev, generator=g) < 0.5] = 0
+    mvs = torch.stack([torch.full_like(cx, 16), torch.full_like(cx, 16), cx + off[..., 0], cy + off[..., 1], cx, cy], -1)
+    mvs = mvs.reshape(Na, T, M, 6).contiguous()
+    counts = torch.full((Na, T), M, dtype=torch.int32, device=dev)
+    ws = torch.empty(Na * ha * wa * 20, dtype=torch.uint8, device=dev)
+    ms = time_ms(lambda: ops.mv_accumulate(mvs, counts, ha, wa, workspace=ws), 2, 5)
+    # algorithmic bytes per GOP: per P-frame read + write the (x,y) int2 field once, plus the vector list
+    alg = T * (2 * ha * wa * 8 + M * 24) + ha * wa * 8
+    r = row("upstream: coviar MV accumulation, %d GOPs x 11 P-frames @720p" % Na, Na, alg, ms, pk, "unit = GOPs")
+    del mvs, counts, ws, off
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -219,6 +241,7 @@ def main():
     ap.add_argument("--only-nhwc", action="store_true")
     ap.add_argument("--only-nhwc-tma", action="store_true")
     ap.add_argument("--only-nocur", action="store_true")
+    ap.add_argument("--only-upstream", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
@@ -227,6 +250,9 @@ def main():
         return
     if args.only_single:
         single_frame_rows(dev, pk)
+        return
+    if args.only_upstream:
+        upstream_rows(dev, pk, args.quick)
         return
     if args.only_nocur:
         nocur_rows(dev, pk)
@@ -294,24 +320,7 @@ def main():
     nhwc_rows(dev, pk, args.quick)
     torch.cuda.empty_cache()
 
-    # ---- upstream (8f rank 3): coviar MV accumulation, 64 GOPs x 11 P-frames at 720p ----
-    Na, T, ha, wa = (16 if args.quick else 64), 11, 720, 1280
-    bx, by = wa // 16, ha // 16
-    M = bx * by
-    g = torch.Generator(device=dev).manual_seed(3)
-    cx = (torch.arange(bx, device=dev, dtype=torch.int32) * 16 + 8).view(1, 1, 1, bx).expand(Na, T, by, bx)
-    cy = (torch.arange(by, device=dev, dtype=torch.int32) * 16 + 8).view(1, 1, by, 1).expand(Na, T, by, bx)
-    off = torch.randint(-16, 17, (Na, T, by, bx, 2), device=dev, generator=g, dtype=torch.int32)
-    off[torch.rand((Na, T, by, bx), device=dev, generator=g) < 0.5] = 0
-    mvs = torch.stack([torch.full_like(cx, 16), torch.full_like(cx, 16), cx + off[..., 0], cy + off[..., 1], cx, cy], -1)
-    mvs = mvs.reshape(Na, T, M, 6).contiguous()
-    counts = torch.full((Na, T), M, dtype=torch.int32, device=dev)
-    ws = torch.empty(Na * ha * wa * 20, dtype=torch.uint8, device=dev)
-    ms = time_ms(lambda: ops.mv_accumulate(mvs, counts, ha, wa, workspace=ws), 2, 5)
-    # algorithmic bytes per GOP: per P-frame read + write the (x,y) int2 field once, plus the vector list
-    alg = T * (2 * ha * wa * 8 + M * 24) + ha * wa * 8
-    r = row("upstream: coviar MV accumulation, %d GOPs x 11 P-frames @720p" % Na, Na, alg, ms, pk, "unit = GOPs")
-    del mvs, counts, ws, off
+    upstream_rows(dev, pk, args.quick)
 
     # ---- config 4: 1080p -> 68x120 ----
     H4, W4 = 68, 120

@@ -507,7 +507,8 @@ int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int
 int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res, int N, int height,
                             int width, void* stream) {
   if (!iframe || !cur || !mv || !res) return fail(LSFA_E_BADARG, "NULL pointer");
-  if (N <= 0 || height <= 0 || width <= 0) return fail(LSFA_E_SHAPE, "bad dims");
+  if (N <= 0 || height <= 0 || width <= 0 || N > 65535 || height > 65535)
+    return fail(LSFA_E_SHAPE, "bad dims (N and height index the launch grid: at most 65535)");
   if (reinterpret_cast<uintptr_t>(mv) % 8) return fail(LSFA_E_ALIGN, "mv must be 8-byte aligned");
   return cuda_result(lsfa::launch_coviar_residual(iframe, cur, mv, res, N, height, width, as_stream(stream)),
                      "coviar_residual launch");

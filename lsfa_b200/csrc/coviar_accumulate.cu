@@ -131,25 +131,18 @@ __global__ void mvacc_finish_kernel(const A* __restrict__ accu, int2* __restrict
 
 // residual (:141-175, accumulate case): res[y][x][c] = cur[y][x][c] - iframe[src_y][src_x][c], src = (x,y) - mv
 __global__ void coviar_residual_kernel(const unsigned char* __restrict__ iframe, const unsigned char* __restrict__ cur,
-                                       const int2* __restrict__ mv, int* __restrict__ res, int N, int height, int width) {
-  const long long hw = (long long)height * width, total = (long long)N * hw;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i / hw);
-    const int p = (int)(i - (long long)n * hw);
-    const int2 m = mv[i];
-    const int sx = p % width - m.x, sy = p / width - m.y;      // always in bounds for an accumulated field
-    const size_t src = ((size_t)n * hw + (size_t)sy * width + sx) * 3;
+                                       const int2* __restrict__ mv, int* __restrict__ res, int height, int width) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= width) return;
+  const size_t frame = (size_t)blockIdx.z * height * width;
+  const size_t i = frame + (size_t)y * width + x;
+  const int2 m = mv[i];
+  const int sx = x - m.x, sy = y - m.y;                  // always in bounds for an accumulated field
+  const size_t src = (frame + (size_t)sy * width + sx) * 3;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) res[i * 3 + c] = (int)cur[i * 3 + c] - (int)iframe[src + c];
-  }
+  for (int c = 0; c < 3; ++c) res[i * 3 + c] = (int)cur[i * 3 + c] - (int)iframe[src + c];
 }
 
-static inline int ew_grid2(long long total, int threads) {
-  long long g = (total + threads - 1) / threads;
-  if (g > 148LL * 16) g = 148LL * 16;
-  if (g < 1) g = 1;
-  return (int)g;
-}
 
 template <typename A>
 static cudaError_t run_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
@@ -183,8 +176,8 @@ cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T
 
 cudaError_t launch_coviar_residual(const unsigned char* iframe, const unsigned char* cur, const int* mv, int* res, int N,
                                    int height, int width, cudaStream_t st) {
-  coviar_residual_kernel<<<ew_grid2((long long)N * height * width, 256), 256, 0, st>>>(
-      iframe, cur, reinterpret_cast<const int2*>(mv), res, N, height, width);
+  const dim3 pg((width + 255) / 256, height, N);
+  coviar_residual_kernel<<<pg, 256, 0, st>>>(iframe, cur, reinterpret_cast<const int2*>(mv), res, height, width);
   return cudaPeekAtLastError();
 }
 

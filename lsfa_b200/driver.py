@@ -45,7 +45,10 @@ class StreamScheduler:
                           **kw) -> torch.Tensor:
         """get_cur_test_symbol for a whole batch (SYM:570-586): out[i] = cur[i] + warp(key_table[slot[i]], mv[i])
         [+ rnet(res[i])].  key_slots: (B,) int array of table slots."""
-        idx = torch.as_tensor(np.asarray(key_slots, dtype=np.int32), device=self.device)
+        if isinstance(key_slots, torch.Tensor):        # already on the device: no copy, no sync (batched harness)
+            idx = key_slots.to(device=self.device, dtype=torch.int32)
+        else:
+            idx = torch.as_tensor(np.asarray(key_slots, dtype=np.int32), device=self.device)
         return ops.warp_scale_aggregate(self.key_table, mv, key_index=idx, cur=cur, res=res, rnet_w=rnet_w,
                                         rnet_b=rnet_b, weight_mode="add", flow_kind=flow_kind, im_scale=im_scale,
                                         out=out, **kw)

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: multi-stream sweep - S independent VID-shaped streams sharded over the GPUs of one box
+(no collective on the data path), each stream one 12-frame video segment = key frame, 10 non-key frames, and the closing frame (which the reference's
+schedule treats as a key frame: core/loader.py:124-127).
+
+One step = the reference's non-key-frame graph as shipped (get_cur_test_symbol, SYM:570-586: warp(key, MV) +
+rnet_conv0(res) + current feature) for EVERY non-key frame of every local stream, batched through
+lsfa_b200.driver.StreamScheduler: one fused launch per batch of `--batch` frames, each frame pointing at its stream's key
+feature through key_index (tile_as without the tile).  The key table holds one fp32 feature per local stream (1024
+streams = 10 GB); the per-frame inputs (raw MV, pooled residual, current feature) come from a pool of `--batch` synthetic
+frames that every launch re-reads (their content does not change the work; the key features are all distinct).
+
+Algorithmic bytes per frame: cur + out + key/10 (a key feature is read once per GOP by design: consecutive frames of a
+batch share it) + 32*HW MV taps + 12*HW residual.  Prints one JSON line per S (rank 0): whole-job frames/s = frames of all
+ranks / max time over ranks.
+
+  python tools/bench_streams.py                       # 1 GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29519 tools/bench_streams.py
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lsfa_b200 import streams  # noqa: E402
+from lsfa_b200.driver import StreamScheduler  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--streams", type=int, nargs="+", default=[64, 256, 1024])
+    ap.add_argument("--batch", type=int, default=80, help="frames per launch (80 = 8 streams x 10 non-key frames)")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    C, H, W, mvh, mvw = 1024, 38, 63, 600, 1000
+    HW, F4 = H * W, C * H * W * 4
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    cur = torch.randn((B, C, H, W), device=dev, generator=g).clamp_(min=0)
+    out = torch.empty_like(cur)
+    blk = torch.randint(-32, 33, (B, (mvh + 15) // 16, (mvw + 15) // 16, 2), device=dev, generator=g, dtype=torch.int32)
+    blk[torch.rand(blk.shape[:3], device=dev, generator=g) < 0.5] = 0
+    mv = blk.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :mvh, :mvw].contiguous()
+    res = torch.randn((B, 3, H, W), device=dev, generator=g) * 30
+    rnet_w = 0.01 * torch.randn((C, 3), device=dev, generator=g)
+    rnet_b = torch.zeros((C,), device=dev)
+    for S in args.streams:
+        seg = [streams.KEY_FRAME_INTERVAL] * S                      # one 12-frame segment per stream: 10 non-key frames
+        sch = StreamScheduler(seg, C, (H, W), dev, rank=rank, world_size=world)
+        sch.key_table.normal_(generator=g).clamp_(min=0)             # every stream its own key feature
+        batches = sch.batches(B)
+        slots = [torch.as_tensor(b[2], dtype=torch.int32, device=dev) for b in batches]
+        frames = sum(len(b[2]) for b in batches)
+
+        def step():
+            for sl in slots:
+                m = sl.numel()
+                sch.run_non_key_batch(sl, mv[:m], cur[:m], res=res[:m], rnet_w=rnet_w, rnet_b=rnet_b, out=out[:m])
+
+        for _ in range(args.warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        tot_frames, max_ms = streams.gather_frame_counts(frames, ms)
+        if rank == 0:
+            alg = 2 * F4 + F4 // 10 + 44 * HW
+            fps = tot_frames / (max_ms / 1e3)
+            print(json.dumps({"config": "cfg5 multi-stream sweep: %d streams x 10 non-key frames, V1 shipped path, shared key per GOP" % S,
+                              "streams": S, "n_gpus": world, "frames_per_step": tot_frames, "launches_per_step_per_gpu": len(slots),
+                              "ms_per_step": round(max_ms, 4), "frames_per_s": round(fps, 1),
+                              "alg_bytes_per_frame": alg, "achieved_gbs_per_gpu": round(fps / world * alg / 1e9, 1),
+                              "frac_of_measured_peak": round(fps / world * alg / 1e9 / peak, 4),
+                              "key_table_gb_per_gpu": round(sch.key_table.numel() * 4 / 1e9, 2)}), flush=True)
+        del sch, slots
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -752,6 +752,14 @@ def test_exact_two_phase_key_frame_graphs(ops, cuda):
     assert np.abs(host(got_f) - want_f).max() <= 2e-4 * scale
     assert np.abs(host(got_q) - want_q).max() <= 2e-4 * scale
     assert np.array_equal(host(got_f)[1], d["cur"][1]) and np.array_equal(host(got_q)[1], d["cur"][1])
+    # the same graphs with the library convolutions in bf16 channels-last (cuDNN's tensor-core path, 3x faster at full
+    # size): only the blend weights move, by the bf16 rounding of the embeddings / quality logits
+    got_fb = graphs.key_frame_fgfa(t(d["key"]), t(d["mv"]), t(d["scale_map"]), t(d["cur"]), [t(a) for a in emb],
+                                   is_first_frame=t(first), flow_kind="raw", conv_dtype=torch.bfloat16)
+    got_qb = graphs.key_frame_nq(t(d["key"]), t(d["mv"]), t(d["scale_map"]), t(d["cur"]), [t(a) for a in nq],
+                                 is_first_frame=t(first), flow_kind="raw", conv_dtype=torch.bfloat16)
+    assert np.abs(host(got_fb) - want_f).max() <= 1e-2 * scale
+    assert np.abs(host(got_qb) - want_q).max() <= 1e-2 * scale
 
 
 def test_stream_scheduler_batches_non_key_frames_of_many_streams(ops, cuda):

@@ -56,7 +56,7 @@ def synth(N, C, H, W, mvh, mvw, dev, max_px=32, E=0):
 
 
 def row(name, frames, alg_bytes_per_frame, ms, pk, note=""):
-    gbs = frames * alg_bytes_per_frame / (ms / 1e3) / 1e9
+    gbs = frames * alg_bytes_per_frame / (ms / 1e3) / 1e9      # 0 for rows that are not byte-bound (library GEMMs)
     r = {"config": name, "frames": frames, "ms_per_step": round(ms, 4), "frames_per_s": round(frames / (ms / 1e3), 1),
          "alg_bytes_per_frame": alg_bytes_per_frame, "achieved_gbs": round(gbs, 1), "frac_of_measured_peak": round(gbs / pk, 4),
          "frac_of_8TBs": round(gbs / 8000.0, 4), "note": note}
@@ -232,6 +232,53 @@ def upstream_rows(dev, pk, quick):
 
 
 
+def keyframe_rows(dev, pk, quick):
+    """Key-frame graphs end to end (SYM:468-477): K1 (lsfa warp x scale) -> embedding / Nq convolutions (LIBRARY GEMMs:
+    cuDNN through torch, as north_star prescribes) -> K2 (lsfa cosine + blend).  Answers SURVEY 8f rank 2's question
+    "do the GEMMs matter": per-phase times; the convolutions in fp32 (TF32 tensor cores) and in bf16."""
+    import torch.nn.functional as F
+    from lsfa_b200 import graphs
+    C, H, W, E = 1024, 38, 63, 2048
+    HW, F4 = H * W, C * H * W * 4
+    N = 8 if quick else 16
+    d = synth(N, C, H, W, 600, 1000, dev)
+    flow = ops.mv_pool(d["mv"])
+    g = torch.Generator(device=dev).manual_seed(5)
+    rn = lambda *sh: 0.01 * torch.randn(sh, device=dev, generator=g)
+    emb = (rn(512, C, 1, 1), rn(512), rn(512, 512, 3, 3), rn(512), rn(E, 512, 1, 1), rn(E))
+    nq = (rn(256, C, 3, 3), rn(256), rn(16, 256, 1, 1), rn(16), rn(1, 16, 1, 1), rn(1))
+    gflop_emb = 2 * N * 2 * HW * (C * 512 + 9 * 512 * 512 + 512 * E) / 1e9
+    gflop_nq = 2 * N * 2 * HW * (9 * C * 256 + 256 * 16 + 16) / 1e9
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    warp = ops.warp_scale_aggregate(d["key"], flow, scale_map=d["scale_map"])
+    x2 = torch.cat([d["cur"], warp], dim=0)
+    row("key frame: K1 warp x scale (lsfa)", N, 3 * F4 + 8 * HW,
+        time_ms(lambda: ops.warp_scale_aggregate(d["key"], flow, scale_map=d["scale_map"], out=warp)), pk)
+    ms = time_ms(lambda: graphs.embed_net(x2, *emb), 2, 5)
+    row("key frame: embedding convs, library, fp32/TF32 (%.0f GFLOP = %.0f TFLOP/s)" % (gflop_emb, gflop_emb / ms), N, 0, ms, pk, "library GEMMs")
+    x2b = x2.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    embb = tuple(t.to(torch.bfloat16) for t in emb)
+    embb = (embb[0].contiguous(memory_format=torch.channels_last), embb[1], embb[2].contiguous(memory_format=torch.channels_last),
+            embb[3], embb[4].contiguous(memory_format=torch.channels_last), embb[5])
+    ms = time_ms(lambda: graphs.embed_net(x2b, *embb), 2, 5)
+    row("key frame: embedding convs, library, bf16 channels-last (%.0f TFLOP/s)" % (gflop_emb / ms), N, 0, ms, pk, "library GEMMs")
+    e = graphs.embed_net(x2, *emb)
+    ec, ew = e[:N].contiguous(), e[N:].contiguous()
+    lg = ops.cosine_logits(ew, ec)
+    row("key frame: K2a cosine logits of the 2048-ch embeddings (lsfa)", N, 2 * E * HW * 4 + 8 * HW, time_ms(lambda: ops.cosine_logits(ew, ec)), pk)
+    outb = torch.empty_like(warp)
+    row("key frame: K2b softmax blend (lsfa)", N, 3 * F4 + 8 * HW, time_ms(lambda: ops.blend_logits(warp, d["cur"], lg, out=outb)), pk)
+    row("key frame: Fgfa graph end to end (K1 + fp32/TF32 convs + K2)", N, 0,
+        time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], emb), 2, 5), pk)
+    row("key frame: Fgfa graph end to end (K1 + bf16 channels-last convs + K2)", N, 0,
+        time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], emb, conv_dtype=torch.bfloat16), 2, 5), pk)
+    ms = time_ms(lambda: graphs.nq_net(x2, *nq), 2, 5)
+    row("key frame: Nq convs, library, fp32/TF32 (%.0f GFLOP = %.0f TFLOP/s)" % (gflop_nq, gflop_nq / ms), N, 0, ms, pk, "library GEMMs")
+    row("key frame: Nq graph end to end (K1 + fp32/TF32 convs + blend), as shipped", N, 0,
+        time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nq), 2, 5), pk)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -242,6 +289,7 @@ def main():
     ap.add_argument("--only-nhwc-tma", action="store_true")
     ap.add_argument("--only-nocur", action="store_true")
     ap.add_argument("--only-upstream", action="store_true")
+    ap.add_argument("--only-keyframe", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
@@ -250,6 +298,9 @@ def main():
         return
     if args.only_single:
         single_frame_rows(dev, pk)
+        return
+    if args.only_keyframe:
+        keyframe_rows(dev, pk, args.quick)
         return
     if args.only_upstream:
         upstream_rows(dev, pk, args.quick)

@@ -21,44 +21,65 @@ import torch.nn.functional as F
 from . import ops
 
 
-def _lowp(x, params, conv_dtype):
-    """Library convolutions in a lower storage type (bf16, channels-last: the tensor-core path of cuDNN).  Measured on
-    16 key frames of 1024x38x63: the embedding convs are 3.15 ms in fp32/TF32 (191 TFLOP/s) and 1.01 ms in bf16
-    (599 TFLOP/s) - 89 % of the Fgfa key-frame graph either way (profiles/README.md).  fp32 stays the default: it is the
-    reference's precision."""
+def prepare_params(params, conv_dtype=None):
+    """Convolution parameters in the storage type / memory format the library convolutions will run in (do this once,
+    not per call: converting the 3x3 weights costs as much as the convolution of a small batch)."""
     if conv_dtype is None or conv_dtype == torch.float32:
-        return x, params
+        return tuple(params)
     cl = torch.channels_last
-    x = x.to(conv_dtype).contiguous(memory_format=cl)
-    params = tuple(p.to(conv_dtype).contiguous(memory_format=cl) if p.dim() == 4 else p.to(conv_dtype) for p in params)
-    return x, params
+    return tuple(p if p.dtype == conv_dtype and (p.dim() != 4 or p.is_contiguous(memory_format=cl))
+                 else (p.to(conv_dtype).contiguous(memory_format=cl) if p.dim() == 4 else p.to(conv_dtype)) for p in params)
 
 
-def embed_net(x: torch.Tensor, w1, b1, w2, b2, w3, b3, conv_dtype=None) -> torch.Tensor:
-    """get_embednet SYM:118-130: 1x1 (C->512) + ReLU, 3x3 (512->512, pad 1) + ReLU, 1x1 (512->2048).
-    Returns float32 NCHW whatever ``conv_dtype`` the library convolutions ran in."""
-    x, (w1, b1, w2, b2, w3, b3) = _lowp(x, (w1, b1, w2, b2, w3, b3), conv_dtype)
+def _lowp_input(feats, conv_dtype):
+    """Concat_0 of float32 NCHW features as ONE bf16 channels-last tensor, written by this package's transpose kernel
+    straight into its slice of the destination (one pass per feature; no float32 concat, no separate cast)."""
+    n = sum(f.shape[0] for f in feats)
+    _, c, h, w = feats[0].shape
+    buf = torch.empty((n, h, w, c), dtype=conv_dtype, device=feats[0].device)
+    at = 0
+    for f in feats:
+        ops.to_nhwc(f, conv_dtype, out=buf[at:at + f.shape[0]])
+        at += f.shape[0]
+    return buf.permute(0, 3, 1, 2)          # logical NCHW, channels-last strides: what cuDNN's tensor-core path wants
+
+
+def embed_net(x: torch.Tensor, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
+    """get_embednet SYM:118-130: 1x1 (C->512) + ReLU, 3x3 (512->512, pad 1) + ReLU, 1x1 (512->2048), in whatever
+    storage type / memory format ``x`` and the parameters have."""
     x = F.relu(F.conv2d(x, w1, b1))
     x = F.relu(F.conv2d(x, w2, b2, padding=1))
-    return F.conv2d(x, w3, b3).float().contiguous()
+    return F.conv2d(x, w3, b3)
 
 
-def nq_net(x: torch.Tensor, w1, b1, w2, b2, w3, b3, conv_dtype=None) -> torch.Tensor:
+def nq_net(x: torch.Tensor, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
     """Nq_net convs SYM:97-101: 3x3 (C->256, pad 1) + ReLU, 1x1 (256->16) + ReLU, 1x1 (16->1)."""
-    x, (w1, b1, w2, b2, w3, b3) = _lowp(x, (w1, b1, w2, b2, w3, b3), conv_dtype)
     x = F.relu(F.conv2d(x, w1, b1, padding=1))
     x = F.relu(F.conv2d(x, w2, b2))
-    return F.conv2d(x, w3, b3).float().contiguous()
+    return F.conv2d(x, w3, b3)
 
 
 def key_frame_fgfa(feat_key_old, flow, scale_map, conv_feat, embed_params, is_first_frame=None,
                    flow_kind="flow", conv_dtype=None, **kw) -> torch.Tensor:
-    """get_key_test_symbol with add_Fgfa_net (SYM:468-470,473-474,477), exact two-phase form."""
+    """get_key_test_symbol with add_Fgfa_net (SYM:468-470,473-474,477), exact two-phase form.
+
+    ``conv_dtype=torch.bfloat16`` runs the library convolutions on cuDNN's bf16 channels-last (tensor-core) path:
+    measured on 16 key frames of 1024x38x63 they take 3.15 ms in fp32/TF32 (191 TFLOP/s) and 1.01 ms in bf16
+    (599 TFLOP/s) - 89 % of this graph in fp32.  The features enter through this package's transpose kernel and the
+    2048-channel embeddings stay bf16 channels-last for the cosine kernel (no float32 copy of them is ever made).
+    fp32 is the default: it is the reference's precision."""
     warp = ops.warp_scale_aggregate(feat_key_old, flow, scale_map=scale_map, flow_kind=flow_kind, **kw)      # K1
-    emb = embed_net(torch.cat([conv_feat, warp], dim=0), *embed_params, conv_dtype=conv_dtype)             # SYM:133-134
     n = conv_feat.shape[0]
-    emb_cur, emb_warp = emb[:n].contiguous(), emb[n:].contiguous()                                         # SYM:135
-    logits = ops.cosine_logits(emb_warp, emb_cur)                                                          # SYM:137-139
+    if conv_dtype is None or conv_dtype == torch.float32:
+        emb = embed_net(torch.cat([conv_feat, warp], dim=0), *embed_params)                                # SYM:133-134
+        emb_cur, emb_warp = emb[:n].contiguous(), emb[n:].contiguous()                                     # SYM:135
+        logits = ops.cosine_logits(emb_warp, emb_cur)                                                      # SYM:137-139
+    else:
+        emb = embed_net(_lowp_input([conv_feat, warp], conv_dtype), *prepare_params(embed_params, conv_dtype))
+        emb = emb.permute(0, 2, 3, 1)                                    # (2N,H,W,E) view of the channels-last result
+        if not emb.is_contiguous():
+            emb = emb.contiguous()
+        logits = ops.cosine_logits(emb[n:], emb[:n], layout="nhwc_bf16")
     # K2: blend the already warped+scaled feature with conv_feat: an identity warp is NOT needed -
     # the fused op takes the warped feature as `key` with zero flow only in the oracle; here we use
     # the logits blend on top of K1's output via the op-by-op tail (one pass over 3F).
@@ -67,9 +88,12 @@ def key_frame_fgfa(feat_key_old, flow, scale_map, conv_feat, embed_params, is_fi
 
 def key_frame_nq(feat_key_old, flow, scale_map, conv_feat, nq_params, is_first_frame=None,
                  flow_kind="flow", conv_dtype=None, **kw) -> torch.Tensor:
-    """get_key_test_symbol with add_Nq_net (shipped, SYM:468-472,477)."""
+    """get_key_test_symbol with add_Nq_net (shipped, SYM:468-472,477).  ``conv_dtype``: see key_frame_fgfa."""
     warp = ops.warp_scale_aggregate(feat_key_old, flow, scale_map=scale_map, flow_kind=flow_kind, **kw)      # K1
     n = conv_feat.shape[0]
-    q = nq_net(torch.cat([warp, conv_feat], dim=0), *nq_params, conv_dtype=conv_dtype)                     # SYM:95-101
+    if conv_dtype is None or conv_dtype == torch.float32:
+        q = nq_net(torch.cat([warp, conv_feat], dim=0), *nq_params)                                        # SYM:95-101
+    else:
+        q = nq_net(_lowp_input([warp, conv_feat], conv_dtype), *prepare_params(nq_params, conv_dtype)).float()
     logits = torch.cat([q[:n], q[n:]], dim=1).contiguous()                                                 # (N,2,H,W): [warp, conv]
     return ops.blend_logits(warp, conv_feat, logits, bypass=is_first_frame)

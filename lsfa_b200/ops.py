@@ -609,12 +609,18 @@ def coviar_residual(iframe: torch.Tensor, cur: torch.Tensor, mv: torch.Tensor) -
     return res
 
 
-def to_nhwc(x: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
-    """(N,C,H,W) f32 -> (N,H,W,C) f32|bf16 with our transpose kernel."""
+def to_nhwc(x: torch.Tensor, dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N,C,H,W) f32 -> (N,H,W,C) f32|bf16 with our transpose kernel (``out``: a contiguous (N,H,W,C) destination,
+    e.g. a slice along N of a larger buffer)."""
     _dev(x, "x", torch.float32)
     N, Cc, H, W = x.shape
     lay = A.LAYOUT_NHWC_BF16 if dtype == torch.bfloat16 else A.LAYOUT_NHWC_F32
-    out = torch.empty((N, H, W, Cc), dtype=dtype, device=x.device)
+    if out is None:
+        out = torch.empty((N, H, W, Cc), dtype=dtype, device=x.device)
+    else:
+        _dev(out, "out", dtype)
+        if tuple(out.shape) != (N, H, W, Cc):
+            raise ValueError("out must be (N,H,W,C)=%s, got %s" % ((N, H, W, Cc), tuple(out.shape)))
     A.check(A.load().lsfa_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), N, Cc, H, W, lay, _stream()))
     return out
 

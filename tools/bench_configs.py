@@ -257,10 +257,9 @@ def keyframe_rows(dev, pk, quick):
         time_ms(lambda: ops.warp_scale_aggregate(d["key"], flow, scale_map=d["scale_map"], out=warp)), pk)
     ms = time_ms(lambda: graphs.embed_net(x2, *emb), 2, 5)
     row("key frame: embedding convs, library, fp32/TF32 (%.0f GFLOP = %.0f TFLOP/s)" % (gflop_emb, gflop_emb / ms), N, 0, ms, pk, "library GEMMs")
-    x2b = x2.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    embb = tuple(t.to(torch.bfloat16) for t in emb)
-    embb = (embb[0].contiguous(memory_format=torch.channels_last), embb[1], embb[2].contiguous(memory_format=torch.channels_last),
-            embb[3], embb[4].contiguous(memory_format=torch.channels_last), embb[5])
+    x2b = graphs._lowp_input([d["cur"], warp], torch.bfloat16)
+    embb = graphs.prepare_params(emb, torch.bfloat16)
+    nqb = graphs.prepare_params(nq, torch.bfloat16)
     ms = time_ms(lambda: graphs.embed_net(x2b, *embb), 2, 5)
     row("key frame: embedding convs, library, bf16 channels-last (%.0f TFLOP/s)" % (gflop_emb / ms), N, 0, ms, pk, "library GEMMs")
     e = graphs.embed_net(x2, *emb)
@@ -272,11 +271,13 @@ def keyframe_rows(dev, pk, quick):
     row("key frame: Fgfa graph end to end (K1 + fp32/TF32 convs + K2)", N, 0,
         time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], emb), 2, 5), pk)
     row("key frame: Fgfa graph end to end (K1 + bf16 channels-last convs + K2)", N, 0,
-        time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], emb, conv_dtype=torch.bfloat16), 2, 5), pk)
+        time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], embb, conv_dtype=torch.bfloat16), 2, 5), pk)
     ms = time_ms(lambda: graphs.nq_net(x2, *nq), 2, 5)
     row("key frame: Nq convs, library, fp32/TF32 (%.0f GFLOP = %.0f TFLOP/s)" % (gflop_nq, gflop_nq / ms), N, 0, ms, pk, "library GEMMs")
     row("key frame: Nq graph end to end (K1 + fp32/TF32 convs + blend), as shipped", N, 0,
         time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nq), 2, 5), pk)
+    row("key frame: Nq graph end to end (K1 + bf16 channels-last convs + blend)", N, 0,
+        time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nqb, conv_dtype=torch.bfloat16), 2, 5), pk)
 
 
 def main():

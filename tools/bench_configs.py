@@ -169,6 +169,24 @@ def nhwc_rows(dev, pk, quick, only_tma=False):
             "ablation" if nm else "")
         p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", layout="nhwc_bf16", force_generic=fg, workspace=ws)
         row("V0 warp only bf16 NHWC batch %d%s" % (Nb, nm), Nb, 2 * F2 + 32 * HW, time_ms(lambda: p.run(s), 3, 10), pk, "ablation" if nm else "")
+    if not only_tma:
+        # config 3's ablation arm: the same computation op by op in the library a user would reach for (PyTorch eager,
+        # bf16 channels-last): grid_sample + mul + softmax + 2 mul + add = 6+ kernels and every intermediate through HBM
+        import torch.nn.functional as F
+        nb = min(Nb, 128)
+        kc, sc, cc = (nh[k][:nb].permute(0, 3, 1, 2) for k in ("key", "scale_map", "cur"))     # logical NCHW, channels-last
+        flow = ops.mv_pool(mvb[:nb])
+        grid = ops.GridGenerator(flow).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)     # (N,H,W,2) as grid_sample wants
+        lg = lgb[:nb]
+
+        def torch_chain():
+            w = F.grid_sample(kc, grid, mode="bilinear", padding_mode="zeros", align_corners=True) * sc
+            a = torch.softmax(lg, dim=1).to(torch.bfloat16)
+            return a[:, 0:1] * w + a[:, 1:2] * cc
+
+        row("cfg3 V2 bf16 NHWC batch %d, UNFUSED: PyTorch eager op by op (grid_sample, mul, softmax, blend)" % nb, nb,
+            4 * F2 + 40 * HW, time_ms(torch_chain, 2, 5), pk, "ablation: algorithmic bytes of the fused op")
+        del kc, sc, cc, flow, grid, lg
     del nh, p, mvb, lgb, resb
     torch.cuda.empty_cache()
     nf = {k: ops.to_nhwc(d[k], torch.float32) for k in ("key", "cur", "scale_map")}

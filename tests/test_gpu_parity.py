@@ -484,6 +484,28 @@ def test_nhwc_all_tma_kernel_random_shapes_match_tile_kernel(ops, cuda):
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (it, N, C, H, W, variant, layout, rep)
 
 
+@pytest.mark.parametrize("layout", ["nhwc_f32", "nhwc_bf16"])
+def test_nhwc_all_tma_kernel_key_plane_of_another_size(ops, cuda, layout):
+    """BilinearSampler semantics in channels-last: the key plane (12x5) and the sampling grid (9x7) differ in size and the
+    grid reaches outside [-1,1] (zero padding); all-TMA kernel = tile kernel bit for bit, both = oracle."""
+    rng = np.random.default_rng(9)
+    N, C, Hk, Wk, H, W = 3, 48, 12, 5, 9, 7
+    key = O.synth_features(rng, (N, C, Hk, Wk))
+    grid = rng.uniform(-1.3, 1.3, size=(N, 2, H, W)).astype(np.float32)
+    bf16 = layout == "nhwc_bf16"
+    if bf16:
+        key = O.bf16_round(key)
+    want = O.bilinear_sampler(key, grid)
+    kt = ops.to_nhwc(dev(key, cuda), torch.bfloat16 if bf16 else torch.float32)
+    outs = [host(ops.to_nchw(ops.warp_scale_aggregate(kt, dev(grid, cuda), flow_kind="grid", layout=layout, force_generic=fg)))
+            for fg in (3, 1)]
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    if bf16:
+        assert_close_bf16(outs[0], want, what="nhwc tma sampler")
+    else:
+        assert_close_f32(outs[0], want, scale=np.abs(key).max(), what="nhwc tma sampler")
+
+
 def test_plane_generic_nhwc_identical_bits(ops, cuda):
     """The three f32 kernels evaluate the same fmaf chain: results must agree bit for bit."""
     d = make_case(33, 3, 64, 38, 63, with_bypass=True)

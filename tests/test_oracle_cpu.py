@@ -181,3 +181,53 @@ def test_algorithmic_bytes_match_survey():
     assert O.algorithmic_bytes_per_frame(1024, 38, 63, 2, "V2") == 19_707_408
     assert O.algorithmic_bytes_per_frame(1024, 38, 63, 4, "V3") == 78_542_352
     assert O.algorithmic_bytes_per_frame(1024, 68, 120, 4, "V2") == 134_019_840
+
+
+def test_oracle_properties_linearity_and_partition_of_unity():
+    """Size-independent properties of a7+a8 the GPU tests rely on at full size: the warp is linear in the key feature,
+    an interior constant plane stays constant (the four tap weights sum to 1), and zero padding only ever shrinks it."""
+    rng = np.random.default_rng(12)
+    N, C, H, W = 2, 5, 14, 17
+    k1, k2 = O.synth_features(rng, (N, C, H, W)), O.synth_features(rng, (N, C, H, W))
+    flow = rng.uniform(-3, 3, size=(N, 2, H, W)).astype(np.float32)
+    a, b = np.float32(0.75), np.float32(-1.5)
+    lhs = O.warp((a * k1 + b * k2).astype(np.float32), flow)
+    rhs = a * O.warp(k1, flow) + b * O.warp(k2, flow)
+    assert np.abs(lhs - rhs).max() <= 1e-5 * max(np.abs(k1).max(), np.abs(k2).max())
+    ones = np.ones((N, C, H, W), np.float32)
+    w = O.warp(ones, flow)
+    assert w.max() <= 1.0 + 1e-6 and w.min() >= 0.0
+    x0, y0, _, _ = O.sampler_coords(O.grid_generator_warp(flow), H, W)
+    inside = (x0 >= 0) & (x0 + 1 <= W - 1) & (y0 >= 0) & (y0 + 1 <= H - 1)
+    assert np.abs(w[:, 0][inside] - 1.0).max() <= 1e-6
+
+
+def test_residual_front_end_matches_cv2_end_to_end():
+    """a1..a5 for the residual (image.py:52,59,205,207-222): the oracle's own float32 resize against cv2's, through the
+    whole chain, for the scales the reference's resize() produces; flip commutes with the chain as image.py:59 applies it."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(21)
+    for (h, w), s in (((96, 160), 1.0), ((48, 80), 2.0), ((90, 160), 0.78125), ((72, 96), 1.25)):
+        res = rng.integers(-64, 65, size=(h, w, 3)).astype(np.float32)
+        mv = np.zeros((h, w, 2), np.float32)
+        ours = O.transform_mv_res(mv, res, s, (1.5, -2.0, 3.25), 0.5)[1]
+        ref = O.transform_mv_res(mv, res, s, (1.5, -2.0, 3.25), 0.5, use_cv2=True)[1]
+        assert ours.shape == ref.shape
+        if s in (1.0, 2.0):
+            assert np.array_equal(ours, ref)
+        else:
+            assert np.abs(ours - ref).max() <= 2e-5 * 64        # cv2 >= 4: another SIMD routine for 3-channel images
+        flipped = O.transform_mv_res(mv, res[:, ::-1], s)[1]
+        assert flipped.shape == ours.shape
+
+
+def test_centre_rows_are_exactly_what_the_stride16_reduction_reads():
+    """The host path sends only rows 16k+7 / 16k+8 of an MV field (lsfa_mv_centre_rows_h2d): zeroing every other row
+    must not change the oracle's pooled flow, for heights with and without a lone last row."""
+    rng = np.random.default_rng(5)
+    for h in (600, 599, 24, 23, 9, 8):
+        mv = rng.integers(-64, 65, size=(1, h, 50, 2), dtype=np.int32)
+        keep = np.zeros_like(mv)
+        rows = [r for r in range(h) if r % 16 in (7, 8)]
+        keep[:, rows] = mv[:, rows]
+        assert np.array_equal(O.mv_pool(mv), O.mv_pool(keep)), h

@@ -106,7 +106,13 @@ def single_frame_rows(dev, pk):
     p2 = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
                                weight_mode="logits", logits=d["logits"])
     row("single frame: fused V2", 1, 4 * F4 + 40 * HW, time_ms(lambda: p2.run(s), 10, 200), pk, "latency, eager")
-    for name, p, b in (("cfg1 single frame: fused warp, raw MV", p0, 2 * F4 + 32 * HW), ("single frame: fused V2", p2, 4 * F4 + 40 * HW)):
+    p0s = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", workspace=False)
+    row("cfg1 single frame: fused warp, raw MV, no scratch (1 launch)", 1, 2 * F4 + 32 * HW, time_ms(lambda: p0s.run(s), 10, 200), pk, "latency, eager")
+    p2s = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
+                                weight_mode="logits", logits=d["logits"], workspace=False)
+    row("single frame: fused V2, no scratch (1 launch)", 1, 4 * F4 + 40 * HW, time_ms(lambda: p2s.run(s), 10, 200), pk, "latency, eager")
+    for name, p, b in (("cfg1 single frame: fused warp, raw MV", p0, 2 * F4 + 32 * HW), ("single frame: fused V2", p2, 4 * F4 + 40 * HW),
+                       ("single frame: fused V2, no scratch", p2s, 4 * F4 + 40 * HW)):
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for _ in range(3):

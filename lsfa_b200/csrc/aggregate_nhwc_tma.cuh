@@ -9,10 +9,12 @@
 //                          static stride without scratch), one lane per pixel does the whole index
 //                          chain (a3/a5/a6 pooling in float64, a7 grid, a8 floor/weights, a13 softmax,
 //                          blend fold) into a ring of record batches in shared memory
-//   warp 1   producer    : per group of G pixels: 2G tap-row copies (one lane each; the two taps of a row are
+//   warps 1-2 producers  : per group of G pixels: 2G tap-row copies (one lane each; the two taps of a row are
 //                          neighbours in memory) + one copy of the scale run + one of the cur run
-//                          HBM/L2 --cp.async.bulk--> stage; a stage is refilled the moment its consumers are done
-//   warps 2+ consumers   : 6 x LDS.128 + packed fp32 math + one 16-byte streaming store per 16 bytes of output
+//                          HBM/L2 --cp.async.bulk--> stage; a stage is refilled the moment its consumers are done;
+//                          producer k issues items k, k+2, ...
+//   warps 3+ consumers   : two groups of 8 warps, group k computes items k, k+2, ... (two stages at once):
+//                          6 x LDS.128 + packed fp32 math + one 16-byte streaming store per 16 bytes of output
 //                          (a pixel's channel run is 16-byte aligned and contiguous: every store instruction
 //                          writes 512 contiguous bytes).  A bulk store from shared memory was measured first:
 //                          the producer then waits ~0.8 us per group for the store to leave the copy engine's

@@ -493,8 +493,9 @@ size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width) {
 int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height, int width,
                            int32_t* mv_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!mvs || !counts || !mv_out || !workspace) return fail(LSFA_E_BADARG, "NULL pointer");
-  if (N <= 0 || T < 0 || M <= 0 || height <= 0 || width <= 0 || N > 65535 || height > 65535)
-    return fail(LSFA_E_SHAPE, "bad dims (N and height index the launch grid: at most 65535)");
+  if (N <= 0 || T < 0 || M <= 0 || height <= 0 || width <= 0 || N > 65535 || height > 65535 ||
+      (long long)height * width >= (1LL << 31))
+    return fail(LSFA_E_SHAPE, "bad dims (N and height index the launch grid: at most 65535; height*width < 2^31)");
   if (workspace_bytes < lsfa_mv_accumulate_workspace_bytes(N, height, width))
     return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", lsfa_mv_accumulate_workspace_bytes(N, height, width));
   if ((reinterpret_cast<uintptr_t>(workspace) % 8) || (reinterpret_cast<uintptr_t>(mv_out) % 8) ||

@@ -55,12 +55,18 @@ __global__ void mvacc_owner_kernel(const MvRec* __restrict__ mvs, const int* __r
   const int bw = x_hi - x_lo, bh = y_hi - y_lo;
   if (bw <= 0 || bh <= 0) return;
   int* own = owner + (size_t)n * height * width;
+  const int val = tag + i + 1;
+  // lanes run along x: 16 neighbouring pixels per 64-byte segment (the reference walks x outer, y inner; the order is
+  // irrelevant here).  Block widths are powers of two in practice (16, 8, 4): shift and mask instead of a division.
+  const int sh = (bw & (bw - 1)) == 0 ? __ffs(bw) - 1 : -1;
   for (int q = threadIdx.x; q < bw * bh; q += blockDim.x) {
-    const int ys = y_lo + q / bw, xs = x_lo + q % bw;           // lanes run along x: 16 neighbouring pixels per 64-byte segment
-                                                                // (the reference walks x outer, y inner; the order is irrelevant here)
+    const int qy = sh >= 0 ? (q >> sh) : q / bw;
+    const int ys = y_lo + qy, xs = x_lo + (q - qy * bw);
     const int dx = mv.dst_x + xs, dy = mv.dst_y + ys, sx = mv.src_x + xs, sy = mv.src_y + ys;
-    if (dy >= 0 && dy < height && dx >= 0 && dx < width && sy >= 0 && sy < height && sx >= 0 && sx < width)
-      atomicMax(own + (size_t)dy * width + dx, tag + i + 1);
+    // one unsigned compare per bound: negative coordinates wrap to large values
+    if ((unsigned)dy < (unsigned)height && (unsigned)dx < (unsigned)width && (unsigned)sy < (unsigned)height &&
+        (unsigned)sx < (unsigned)width)
+      atomicMax(own + dy * width + dx, val);
   }
 }
 
@@ -80,26 +86,33 @@ mvacc_gather_kernel(const MvRec* __restrict__ mvs, const A* __restrict__ accu_ol
                     int* __restrict__ owner, int t, int T, int M, int height, int width, int tag) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * kGatherRows, n = blockIdx.z;
   if (x >= width) return;
+  // per-frame base pointers + 32-bit offsets inside the frame (height * width < 2^31 is checked by the entry point):
+  // the 64-bit index arithmetic of a flat layout made this kernel issue bound (ncu: issue_active 79 %)
   const size_t frame = (size_t)n * height * width;
-  const MvRec* list = mvs + ((size_t)n * T + t) * M;
+  const A* __restrict__ ao = accu_old + frame;
+  A* __restrict__ an = accu_new + frame;
+  int* __restrict__ ow = owner + frame;
+  const int2* __restrict__ list = reinterpret_cast<const int2*>(mvs + ((size_t)n * T + t) * M);   // 3 x int2 per vector
+  const int rows = min(kGatherRows, height - y0);
+  const int i0 = y0 * width + x;
+  const int tagv = tag >> 24;
   int o[kGatherRows];
   A v[kGatherRows];
 #pragma unroll
   for (int u = 0; u < kGatherRows; ++u) {                // round 1: owner + own value
     o[u] = 0;
-    if (y0 + u < height) {
-      const size_t i = frame + (size_t)(y0 + u) * width + x;
-      o[u] = owner[i];
-      v[u] = accu_old[i];
+    if (u < rows) {
+      o[u] = ow[i0 + u * width];
+      v[u] = ao[i0 + u * width];
     }
   }
   int2 ms[kGatherRows], md[kGatherRows];
 #pragma unroll
   for (int u = 0; u < kGatherRows; ++u) {                // round 2: the owning vector's src and dst
-    if (tag) o[u] = (o[u] >> 24) == (tag >> 24) ? (o[u] & 0xffffff) : 0;       // entries of earlier frames are stale
+    if (tag) o[u] = (o[u] >> 24) == tagv ? (o[u] & 0xffffff) : 0;       // entries of earlier frames are stale
     ms[u] = md[u] = make_int2(0, 0);
     if (o[u] > 0) {
-      const int2* rec = reinterpret_cast<const int2*>(list + (o[u] - 1));
+      const int2* rec = list + 3 * (o[u] - 1);
       ms[u] = __ldg(rec + 1);                            // (src_x, src_y)
       md[u] = __ldg(rec + 2);                            // (dst_x, dst_y)
     }
@@ -108,14 +121,13 @@ mvacc_gather_kernel(const MvRec* __restrict__ mvs, const A* __restrict__ accu_ol
   for (int u = 0; u < kGatherRows; ++u)                  // round 3: the gather proper
     if (o[u] > 0) {
       const int sx = ms[u].x + (x - md[u].x), sy = ms[u].y + (y0 + u - md[u].y);
-      v[u] = accu_old[frame + (size_t)sy * width + sx];
+      v[u] = ao[sy * width + sx];
     }
 #pragma unroll
   for (int u = 0; u < kGatherRows; ++u)
-    if (y0 + u < height) {
-      const size_t i = frame + (size_t)(y0 + u) * width + x;
-      accu_new[i] = v[u];
-      if (!tag && o[u] > 0) owner[i] = 0;
+    if (u < rows) {
+      an[i0 + u * width] = v[u];
+      if (!tag && o[u] > 0) ow[i0 + u * width] = 0;
     }
 }
 

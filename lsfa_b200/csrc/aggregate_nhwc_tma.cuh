@@ -13,7 +13,8 @@
 //                          neighbours in memory) + one copy of the scale run + one of the cur run
 //                          HBM/L2 --cp.async.bulk--> stage; a stage is refilled the moment its consumers are done;
 //                          producer k issues items k, k+2, ...
-//   warps 3+ consumers   : two groups of 8 warps, group k computes items k, k+2, ... (two stages at once):
+//   warps 3+ consumers   : 16 warps as two groups of 8 (group k computes items k, k+2, ...: two stages at once) or, for
+//                          the residual variant, one group of 16:
 //                          6 x LDS.128 + packed fp32 math + one 16-byte streaming store per 16 bytes of output
 //                          (a pixel's channel run is 16-byte aligned and contiguous: every store instruction
 //                          writes 512 contiguous bytes).  A bulk store from shared memory was measured first:
@@ -32,8 +33,12 @@
 
 namespace lsfa {
 
-constexpr int kNtConsumerWarps = 8;   // warps per consumer group (all of them work on one stage)
-constexpr int kNtGroups = 2;          // consumer groups: group k takes items k, k+2, ... so two stages are computed at once
+constexpr int kNtAllConsumerWarps = 16;   // consumer warps of the CTA
+// They work as NtPlan::groups groups (1 or 2): a group computes one stage together, group k takes items k, k+groups, ...
+// Same-box A/B (fraction of the copy peak; bf16 batch 512 / 68x120 bf16 / fp32 / shipped non-key bf16 / warp alone bf16):
+//   2 groups of 8: 0.944 / 0.94 / 0.995 / 0.74 / 0.71        1 group of 16: 0.926 / 0.925 / 0.984 / 0.775 / 0.635
+// -> two groups, except for the residual variant (one pass in flight per warp there: 16 warps on a stage hide more).
+constexpr int kNtMaxGroups = 2;
 #ifndef LSFA_NT_PRODUCERS
 #define LSFA_NT_PRODUCERS 2
 #endif
@@ -44,10 +49,10 @@ constexpr int kNtFirstConsumer = 1 + kNtProducers;
 // depth is a multiple of both counts.  That is what makes the parity waits safe: a warp that waits for "the previous
 // use of stage s" created that use's predecessor itself, so the barrier is never two phases behind (a parity wait
 // on a barrier two phases behind returns at once).
-constexpr int kNtStageMultiple = (kNtProducers % kNtGroups == 0) ? kNtProducers
-                               : (kNtGroups % kNtProducers == 0) ? kNtGroups : kNtProducers * kNtGroups;
+constexpr int kNtStageMultiple = (kNtProducers % kNtMaxGroups == 0) ? kNtProducers
+                               : (kNtMaxGroups % kNtProducers == 0) ? kNtMaxGroups : kNtProducers * kNtMaxGroups;
 static_assert(kNtStageMultiple <= 8, "producer / consumer-group counts need too deep a ring");
-constexpr int kNtThreads = (kNtFirstConsumer + kNtGroups * kNtConsumerWarps) * 32;
+constexpr int kNtThreads = (kNtFirstConsumer + kNtAllConsumerWarps) * 32;
 constexpr int kNtMaxStages = 8;     // stages actually used: NtPlan::stages (ring budget / stage size)
 constexpr int kNtRecRing = 4;       // record batches in flight ahead of the producer
 constexpr int kNtMaxG = 8;          // pixels per stage, at most
@@ -88,6 +93,7 @@ struct NtPlan {
   int G;                    // pixels per stage (power of two, <= 8)
   int stages;               // ring depth (<= kNtMaxStages)
   int merge_pairs;          // the two taps of a row travel as one copy when they are neighbours in memory
+  int groups;               // consumer groups (1 or 2)
   unsigned slot;            // bytes of one pixel's channel run
   unsigned stage_bytes;
   unsigned off_scale, off_io;
@@ -121,7 +127,7 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&done[s], kNtConsumerWarps);
+      mbar_init(&done[s], kNtAllConsumerWarps / Q.groups);
     }
     for (int s = 0; s < kNtRecRing; ++s) {
       mbar_init(&rec_full[s], 1);
@@ -274,7 +280,7 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
       if (++rs == kNtRecRing) rs = 0;
     }
     // one stop marker per consumer group: in the slots of items j and j+1 (once their previous items are consumed)
-    for (int k = 0; k < kNtGroups; ++k) {
+    for (int k = 0; k < Q.groups; ++k) {
       const bool mine = turn == pk;
       if (++turn == kNtProducers) turn = 0;
       if (mine) {
@@ -293,8 +299,9 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
   }
 
   // ===================================== consumer warps =====================================
-  const int cgrp = (warp - kNtFirstConsumer) / kNtConsumerWarps;      // consumer group: items cgrp, cgrp + kNtGroups, ...
-  const int cw = (warp - kNtFirstConsumer) % kNtConsumerWarps;
+  const int gw = kNtAllConsumerWarps / Q.groups;       // warps per consumer group
+  const int cgrp = (warp - kNtFirstConsumer) / gw;     // consumer group: items cgrp, cgrp + groups, ...
+  const int cw = (warp - kNtFirstConsumer) % gw;
   const int VP = (int)(slot / 16u);                    // 16-byte vectors per pixel
   const int PPX = (VP + 31) / 32;                      // warp passes per pixel
   // FQ (residual variant only): the passes of a pixel divide the consumer warps, so a warp always works on the same
@@ -324,7 +331,6 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
       rbp[i] = pair2(a[3], b[3]);
     }
   }
-  const int pass0 = cw, pstep = kNtConsumerWarps;      // pass = pixel * PPX + q: q = pass % PPX stays cw % PPX when fixed_q
   T* __restrict__ out = static_cast<T*>(P.out);
   constexpr int NF = has_res ? 1 : 2;                  // passes in flight (the residual variant holds 4*L weights in registers)
   const int ppx_shift = (PPX & (PPX - 1)) == 0 ? __ffs(PPX) - 1 : -1;   // passes per pixel is normally a power of two
@@ -339,7 +345,7 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
     T* obase = out + desc[s].out_elem;
     const int passes = np * PPX;
 #pragma unroll 1
-    for (int pass0 = cw; pass0 < passes; pass0 += NF * kNtConsumerWarps) {
+    for (int pass0 = cw; pass0 < passes; pass0 += NF * gw) {   // pass = pixel * PPX + q: q stays cw % PPX when FQ
       // NF passes of this warp in flight: all shared-memory reads first, then the arithmetic and the stores
       uint4 d[NF][6];
       NtPixW w[NF];
@@ -347,7 +353,7 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
       int vv[NF], gg[NF];
 #pragma unroll
       for (int h = 0; h < NF; ++h) {
-        const int pass = pass0 + h * kNtConsumerWarps;
+        const int pass = pass0 + h * gw;
         const int g = ppx_shift >= 0 ? (pass >> ppx_shift) : pass / PPX;
         const int v = (pass - g * PPX) * 32 + lane;
         gg[h] = g;
@@ -423,8 +429,8 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&done[s]);              // every shared-memory read of the stage is complete
-    s += kNtGroups;
-    if (s >= S) {                                      // S >= kNtGroups: at most one wrap per step
+    s += Q.groups;
+    if (s >= S) {                                      // S >= groups: at most one wrap per step
       s -= S;
       ph ^= 1u;
     }
@@ -450,6 +456,8 @@ inline bool plan_nhwc_tma(const AggParams& P, bool bf16, int var, NtPlan* Q) {
   }
   Q->G = G;
   Q->merge_pairs = getenv("LSFA_NT_NO_MERGE") ? 0 : 1;
+  Q->groups = var == kVarResCur ? 1 : 2;
+  if (const char* e = getenv("LSFA_NT_GROUPS")) Q->groups = atoi(e) == 1 ? 1 : 2;
   Q->slot = (unsigned)slot;
   Q->off_scale = 4u * (unsigned)G * (unsigned)slot;
   Q->off_io = Q->off_scale + (has_scale ? (unsigned)G * (unsigned)slot : 0u);
@@ -478,7 +486,8 @@ cudaError_t launch_nhwc_tma_variant(const AggParams& P, const NtPlan& Q, int gri
   if constexpr (VAR == kVarResCur) {
     const int ppx = ((int)(Q.slot / 16u) + 31) / 32;            // warp passes per pixel
     const int L = (int)(16 / sizeof(T));
-    if (ppx <= kNtConsumerWarps && kNtConsumerWarps % ppx == 0 && P.C % (2 * L) == 0)
+    const int gw = kNtAllConsumerWarps / Q.groups;
+    if (ppx <= gw && gw % ppx == 0 && P.C % (2 * L) == 0)
       return launch_nhwc_tma_fq<T, VAR, true>(P, Q, grid, st);
   }
   return launch_nhwc_tma_fq<T, VAR, false>(P, Q, grid, st);

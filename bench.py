@@ -250,6 +250,10 @@ def run_ours(args):
     frames = args.frames
     K, Wm = args.steps, max(args.warmup, 3)
 
+    # one process per GPU: stay on the CPUs (and memory) of the GPU's NUMA node before any pinned buffer is allocated
+    from lsfa_b200.host import bind_near_gpu
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local) if os.environ.get("LSFA_BENCH_NO_NUMA_BIND") is None else {"bound": False, "skipped": True}
     host = make_host_inputs(frames, seed=1000 + rank)
     d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     torch.cuda.synchronize()
@@ -324,9 +328,14 @@ def run_ours(args):
     bi, bo = agg.bytes_per_call()
     e2e = {"value": e2e_frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "launches_per_step": agg.launches // max(1, e2e_steps),
+           "host_numa_binding_rank0": numa,
            "api": "lsfa_b200.host.HostAggregator (pinned host in/out, %d-frame chunks, 3-stream pipeline; of each "
                   "600x1000 MV field only the 2 rows in 16 the reference's stride-16 resize reads cross PCIe)" % agg.chunk}
     checksum = float(out_host[0, 0, 0, :8].sum())    # the result really is on the host
+    try:
+        os.sched_setaffinity(0, affinity0)           # the CPU baseline below gets every host core back
+    except OSError:
+        pass
 
     extra = {}
     if rank == 0 and not args.no_extra:

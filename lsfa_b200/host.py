@@ -112,3 +112,37 @@ class HostAggregator:
         self.s_in.synchronize()
         self.s_run.synchronize()
         self.s_out.synchronize()
+
+
+def bind_near_gpu(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs ``local_cpulist`` of its PCI
+    function), so that pinned host buffers allocated afterwards are first-touched on that node and the H2D/D2H copies do
+    not cross the socket interconnect.  With one process per GPU (the reference's one-thread-per-GPU model,
+    tester.py:301-309) and PCIe-bound transfers this is what keeps the per-GPU host bandwidth when several ranks copy at
+    once.  Best effort: returns what it did; never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        info["pci"] = bus
+        with open(base + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        info["cpus_local"] = len(cpus)
+        if allowed and allowed != os.sched_getaffinity(0):
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+        info["cpus_now"] = len(os.sched_getaffinity(0))
+    except Exception as e:       # no sysfs / no NUMA information / not permitted: stay as we are
+        info["error"] = repr(e)
+    return info

@@ -89,3 +89,18 @@ def test_world_size_2_gloo_bookkeeping(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert "OK" in outs[0][0]
+
+
+def test_bind_near_gpu_is_best_effort_without_a_gpu():
+    """host.bind_near_gpu never raises: without a CUDA device (or without NUMA information in sysfs) it reports why and
+    leaves the process affinity alone."""
+    import os
+    pytest = __import__("pytest")
+    pytest.importorskip("torch")
+    from lsfa_b200.host import bind_near_gpu
+    before = os.sched_getaffinity(0)
+    info = bind_near_gpu(0)
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

@@ -285,6 +285,36 @@ LSFA_API int lsfa_warp_backward_f32(const float* key, const float* flow, const f
                                     float* grad_flow, int N, int C, int H, int W, int req_key, int req_flow,
                                     void* workspace, size_t workspace_bytes, int kernel, void* stream);
 
+/* ---- the embedding / quality networks of the key-frame aggregation on tensor cores ----
+ * Hand-written sm_100a implicit-GEMM convolutions (tcgen05.mma, fp32 accumulators in tensor memory, operands by
+ * TMA tensor copies; lsfa_b200/csrc/conv_gemm_tc.cu).  Stated-tolerance variant: bf16 operands, fp32 accumulate
+ * (the reference runs these convolutions in fp32 on cuDNN).  Activations are channels-last bf16 (NB,H,W,C);
+ * NB must be even: the reference always convolves Concat_0 of two N-batches (SYM:95,133) and the kernel pairs
+ * image b with image b + NB/2 on one weight tile.  Cin % 64 == 0, Cout % 256 == 0.
+ *
+ * weights: lsfa_pack_conv_weight_bf16 turns MXNet's (Cout,Cin,k,k) float32 into (Cout, k*k*Cin) bf16 (once per
+ * parameter set).  bias stays float32. */
+LSFA_API int lsfa_pack_conv_weight_bf16(const float* w, void* w_packed, int Cout, int Cin, int ksize, void* stream);
+/* mx.sym.Convolution(kernel=(k,k), pad=(k/2,k/2), stride 1, no_bias=False) [+ Activation('relu')]: out (NB,H,W,Cout) bf16 */
+LSFA_API int lsfa_conv_bf16_nhwc(const void* x, const void* w_packed, const float* bias, void* out, int NB, int H, int W,
+                                 int Cin, int Cout, int ksize, int relu, void* stream);
+/* get_embednet (SYM:118-130) + compute_weight (SYM:111-116) of Fgfa_net (SYM:132-139):
+ * x = Concat_0(conv_feat, warp_feat) (2N,H,W,C) bf16 -> logits (N,2,H,W) f32, [n,0] = <e_warp^,e_cur^>, [n,1] = <e_cur^,e_cur^>
+ * (the layout lsfa_blend_logits_f32 / LSFA_W_LOGITS consume).  em_conv3's 2048-channel output is reduced in the
+ * GEMM epilogue and never written.  w1 (C1,C) 1x1, w2 (C2, 9*C1) 3x3, w3 (E, C2) 1x1, packed bf16.
+ * workspace: lsfa_embed_cosine_logits_workspace_bytes, 256-byte aligned, no initialisation needed. */
+LSFA_API size_t lsfa_embed_cosine_logits_workspace_bytes(int N, int H, int W, int C1, int C2, int E);
+LSFA_API int lsfa_embed_cosine_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, const void* w2,
+                                                const float* b2, const void* w3, const float* b3, float* logits,
+                                                int N, int H, int W, int C, int C1, int C2, int E, void* workspace,
+                                                size_t workspace_bytes, void* stream);
+/* the convolutions of Nq_net (SYM:95-101): x = Concat_0(warp_feat, conv_feat) (2N,H,W,C) bf16 -> logits (N,2,H,W) f32,
+ * [n,0] = quality of the warped feature, [n,1] of the current one.  w1 = Nq_conv1 (256, 9*C) packed bf16; the
+ * 256->16->1 tail (w2 (16,256), b2 (16), w3 (16), b3 (1), float32 device arrays) runs in the GEMM epilogue. */
+LSFA_API int lsfa_nq_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, const float* w2, const float* b2,
+                                      const float* w3, const float* b3, float* logits, int N, int H, int W, int C,
+                                      void* stream);
+
 /* layout helpers for the harness: NCHW f32 <-> NHWC {f32,bf16} */
 LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout,
                       void* stream);

@@ -94,6 +94,11 @@ PROTOTYPES = {
     "lsfa_bilinear_sampler_backward_num_launches": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _SZ, _I]),
     "lsfa_grid_generator_warp_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "lsfa_warp_backward_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _SZ, _I, _P]),
+    "lsfa_pack_conv_weight_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "lsfa_conv_bf16_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "lsfa_embed_cosine_logits_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
+    "lsfa_embed_cosine_logits_bf16_nhwc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
+    "lsfa_nq_logits_bf16_nhwc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lsfa_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lsfa_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "lsfa_device.cuh"
+#include "conv_gemm_tc.h"
 
 namespace lsfa {
 // aggregate_nchw.cu
@@ -592,6 +593,91 @@ int lsfa_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, i
   return cuda_result(lsfa::launch_nhwc_to_nchw(src, dst, N, C, H * W, src_layout == LSFA_LAYOUT_NHWC_BF16,
                                                as_stream(stream)),
                      "nhwc_to_nchw launch");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the embedding / quality networks on tensor cores (conv_gemm_tc.cu)
+// ---------------------------------------------------------------------------------------------------------
+static int tc_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    return 148;
+  return n;
+}
+static int tc_result(const char* msg, const char* what) {
+  if (msg) return fail(LSFA_E_UNSUPPORTED, "%s: %s", what, msg);
+  return cuda_result(cudaPeekAtLastError(), what);
+}
+
+int lsfa_pack_conv_weight_bf16(const float* w, void* w_packed, int Cout, int Cin, int ksize, void* stream) {
+  if (!w || !w_packed) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (Cout <= 0 || Cin <= 0 || (ksize != 1 && ksize != 3)) return fail(LSFA_E_SHAPE, "bad dims (ksize must be 1 or 3)");
+  lsfa::tc::launch_pack_weight(w, w_packed, Cout, Cin, ksize * ksize, as_stream(stream));
+  return cuda_result(cudaPeekAtLastError(), "pack_conv_weight launch");
+}
+
+int lsfa_conv_bf16_nhwc(const void* x, const void* w_packed, const float* bias, void* out, int NB, int H, int W, int Cin,
+                        int Cout, int ksize, int relu, void* stream) {
+  if (!x || !w_packed || !bias || !out) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  if (ksize != 1 && ksize != 3) return fail(LSFA_E_SHAPE, "ksize must be 1 or 3");
+  if (reinterpret_cast<uintptr_t>(out) & 15) return fail(LSFA_E_ALIGN, "out must be 16-byte aligned");
+  lsfa::tc::ConvParams P{};
+  P.NB = NB; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.taps = ksize * ksize;
+  P.bias = bias;
+  P.out = static_cast<__nv_bfloat16*>(out);
+  return tc_result(lsfa::tc::launch_conv(x, w_packed, P, relu ? lsfa::tc::EPI_STORE_RELU : lsfa::tc::EPI_STORE, tc_sm_count(),
+                                         as_stream(stream)),
+                   "conv_bf16_nhwc");
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t lsfa_embed_cosine_logits_workspace_bytes(int N, int H, int W, int C1, int C2, int E) {
+  if (N <= 0 || H <= 0 || W <= 0 || C1 <= 0 || C2 <= 0 || E <= 0) return 0;
+  const size_t px = (size_t)2 * N * H * W;
+  return align256(px * C1 * 2) + align256(px * C2 * 2) + align256((size_t)(E / 256) * 3 * N * H * W * 4);
+}
+
+int lsfa_embed_cosine_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                                       const void* w3, const float* b3, float* logits, int N, int H, int W, int C, int C1,
+                                       int C2, int E, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !logits || !workspace) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C1 <= 0 || C2 <= 0 || E <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  if (E % 256) return fail(LSFA_E_SHAPE, "E must be a multiple of 256");
+  const size_t need = lsfa_embed_cosine_logits_workspace_bytes(N, H, W, C1, C2, E);
+  if (workspace_bytes < need) return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", need);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(LSFA_E_ALIGN, "workspace must be 256-byte aligned");
+  const size_t px = (size_t)2 * N * H * W;
+  char* ws = static_cast<char*>(workspace);
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(ws + align256(px * C1 * 2));
+  float* partial = reinterpret_cast<float*>(ws + align256(px * C1 * 2) + align256(px * C2 * 2));
+  const int sms = tc_sm_count();
+  cudaStream_t st = as_stream(stream);
+  lsfa::tc::ConvParams P{};
+  P.NB = 2 * N; P.H = H; P.W = W;
+  // em_conv1 + em_ReLU1 (SYM:119-121)
+  P.Cin = C; P.Cout = C1; P.taps = 1; P.bias = b1; P.out = h1;
+  if (int r = tc_result(lsfa::tc::launch_conv(x, w1, P, lsfa::tc::EPI_STORE_RELU, sms, st), "em_conv1")) return r;
+  // em_conv2 + em_ReLU2 (SYM:123-125)
+  P.Cin = C1; P.Cout = C2; P.taps = 9; P.bias = b2; P.out = h2;
+  if (int r = tc_result(lsfa::tc::launch_conv(h1, w2, P, lsfa::tc::EPI_STORE_RELU, sms, st), "em_conv2")) return r;
+  // em_conv3 (SYM:127-128) with compute_weight's reductions (SYM:111-116) as its epilogue
+  P.Cin = C2; P.Cout = E; P.taps = 1; P.bias = b3; P.out = nullptr; P.partial = partial;
+  if (int r = tc_result(lsfa::tc::launch_conv(h2, w3, P, lsfa::tc::EPI_COSINE, sms, st), "em_conv3+cosine")) return r;
+  lsfa::tc::launch_cosine_finalize(partial, logits, E / 256, N, H * W, st);
+  return cuda_result(cudaPeekAtLastError(), "cosine finalize launch");
+}
+
+int lsfa_nq_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                             const float* b3, float* logits, int N, int H, int W, int C, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !logits) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  lsfa::tc::ConvParams P{};
+  P.NB = 2 * N; P.H = H; P.W = W; P.Cin = C; P.Cout = 256; P.taps = 9;
+  P.bias = b1; P.logits = logits; P.nq_w2 = w2; P.nq_b2 = b2; P.nq_w3 = w3; P.nq_b3 = b3;
+  return tc_result(lsfa::tc::launch_conv(x, w1, P, lsfa::tc::EPI_NQ, tc_sm_count(), as_stream(stream)), "nq_logits");
 }
 
 }  // extern "C"

@@ -1,0 +1,482 @@
+// conv_gemm_tc.cu - the embedding / quality networks of the key-frame aggregation on Blackwell tensor cores.
+//
+// `get_embednet` (SYM:118-130: em_conv1 1x1 1024->512 +ReLU, em_conv2 3x3 512->512
+// +ReLU, em_conv3 1x1 512->2048), `compute_weight` (SYM:111-116: channel L2 norm + dot) and the convolutions of
+// `Nq_net` (SYM:94-101: Nq_conv1 3x3 1024->256 +ReLU, Nq_conv2 1x1 256->16 +ReLU, Nq_conv3 1x1 16->1).
+// SYM = dff_rfcn/symbols/resnet_v1_101_flownet_rfcn.py.
+//
+// One warp-specialised, persistent implicit-GEMM kernel (bf16 operands, fp32 accumulation in tensor memory):
+//   * activations are channels-last bf16 (NB,H,W,Cin) read through a 4-D TMA tensor map (C,W,H,NB): a tile of
+//     128 output pixels is a BW x BH window of one image, and tap (dy,dx) of a 3x3 convolution is the SAME box
+//     shifted by (dx-1,dy-1) - the copy engine zero-fills what falls outside the image, which IS the
+//     convolution's zero padding: no im2col buffer, no halo code.  A 1x1 convolution is the 1-tap case.
+//   * weights are (Cout, taps*Cin) bf16, K-major, read through a 2-D tensor map.
+//   * every CTA works on a PAIR of 128-pixel tiles that share each weight tile: the same window of image b and
+//     of image b + NB/2.  The reference always convolves Concat_0(cur, warp) (SYM:95,133), so the pair is
+//     "this pixel of the current feature and of the warped feature".  Two M=128 accumulators of N=256 fp32
+//     columns fill the SM's 512 tensor-memory columns; per 64-deep k-step the CTA loads 2 x 16 KB of
+//     activations + 32 KB of weights for 2 x 128 x 256 x 64 MACs (128 flop per byte of L2 traffic).
+//   * warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane), warp 2 = tensor-memory
+//     allocator, warps 4-7 = epilogue: thread r owns accumulator row r (tcgen05.ld 32x32b), so every per-pixel
+//     reduction over channels is a private register sum - no shuffles, no shared memory.
+//   * epilogues: bias(+ReLU) -> bf16 store (em_conv1/2);  COSINE (em_conv3): sum e_cur^2, sum e_warp^2,
+//     sum e_warp*e_cur over this CTA's 256 output channels -> 3 floats per pixel; the 2048-channel embeddings
+//     never leave the SM (the reference round-trips 2 x 19.6 MB per frame through HBM for them);
+//     NQ (Nq_conv1): bias+ReLU, then the 256->16 (+ReLU) ->1 tail per pixel in registers -> the logit itself.
+//
+// SASS of this file shows UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (cp.async.bulk.tensor), SYNCS (mbarrier).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lsfa_device.cuh"
+#include "conv_gemm_tc.h"
+
+namespace lsfa {
+namespace tc {
+
+constexpr int BM = 128;                 // pixels per accumulator = tensor-memory lanes
+constexpr int BN = 256;                 // output channels per work item = fp32 columns per accumulator
+constexpr int BK = 64;                  // bf16 per k-step = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * BK * 2;    // 16 KB
+constexpr int B_BYTES = BN * BK * 2;    // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;   // 64 KB
+constexpr int NQ_MID = 16;              // Nq_conv2 width (SYM:99)
+constexpr int EPI_SMEM_FLOATS = BN + NQ_MID * BN + 3 * NQ_MID + 16;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 128 /*barriers*/;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers (tcgen05 / TMA tensor copies).  mbarrier helpers come from lsfa_device.cuh.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major operand whose rows are 128 B (64 bf16) in the SWIZZLE_128B pattern the TMA
+// wrote: 8-row atoms of 1024 B, stride between atoms (SBO) 1024 B, LBO unused for swizzled K-major; version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor of kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4)                 // c_format  = F32
+         | (1u << 7)               // a_format  = BF16
+         | (1u << 10)              // b_format  = BF16
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Item {
+  int chunk, img0, img1, x0, y0;
+};
+__device__ __forceinline__ Item decode_item(const ConvParams& P, int item) {
+  Item it;
+  it.chunk = item % P.n_chunks;
+  int t = item / P.n_chunks;
+  const int tile = t % (P.tiles_x * P.tiles_y);
+  it.img0 = t / (P.tiles_x * P.tiles_y);
+  it.img1 = it.img0 + P.NB / 2;
+  it.x0 = (tile % P.tiles_x) * P.BW;
+  it.y0 = (tile / P.tiles_x) * P.BH;
+  return it;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [BN]
+  float* s_w2t = s_bias + BN;                                                 // NQ: [BN][16] (transposed Nq_conv2 weight)
+  float* s_nq = s_w2t + NQ_MID * BN;                                          // NQ: b2[16], w3[16], b3
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4);
+  uint64_t* full = bars;                    // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;          // [STAGES] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;  // MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 1;     // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = P.num_items;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (EPI == EPI_NQ && warp >= 4) {          // the per-pixel tail's parameters: once per CTA
+    const int t = threadIdx.x - 128;
+    for (int i = t; i < NQ_MID * BN; i += 128) {
+      const int j = i / BN, c = i % BN;       // global (16, 256) row-major -> smem [c][j]
+      s_w2t[c * NQ_MID + j] = P.nq_w2[i];
+    }
+    if (t < NQ_MID) {
+      s_nq[t] = P.nq_b2[t];
+      s_nq[NQ_MID + t] = P.nq_w3[t];
+    }
+    if (t == 0) s_nq[2 * NQ_MID] = P.nq_b3[0];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const Item it = decode_item(P, item);
+        for (int ks = 0; ks < P.k_steps; ++ks) {
+          const int tap = ks / P.kc_per_tap, kc = ks - tap * P.kc_per_tap;
+          const int dy = P.taps == 9 ? tap / 3 - 1 : 0, dx = P.taps == 9 ? tap % 3 - 1 : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          tma_load_4d(st, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, it.img0, &full[stage]);
+          tma_load_4d(st + A_BYTES, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, it.img1, &full[stage]);
+          tma_load_2d(st + 2 * A_BYTES, &tmB, tap * P.Cin + kc * BK, it.chunk * BN, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        mbar_wait(tmem_empty, tphase ^ 1);        // the epilogue has drained both accumulators
+        tcgen05_fence_after();
+        for (int ks = 0; ks < P.k_steps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t da0 = make_kmajor_sw128_desc(a0);
+          const uint64_t da1 = make_kmajor_sw128_desc(a0 + A_BYTES);
+          const uint64_t db = make_kmajor_sw128_desc(a0 + 2 * A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) start-address field
+            umma_bf16(tmem_base, da0 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+            umma_bf16(tmem_base + BN, da1 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty[stage]);             // frees the stage once these MMAs have read it
+          if (ks == P.k_steps - 1) umma_commit(tmem_full);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: thread r owns accumulator row r =====================
+    const int ew = warp - 4;                       // == warp % 4: the tensor-memory lane quarter this warp may read
+    const int row = ew * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    uint32_t tphase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const Item it = decode_item(P, item);
+      epi_bar_sync();                              // previous item's readers of s_bias are done
+      for (int i = threadIdx.x - 128; i < BN; i += 128) s_bias[i] = P.bias[it.chunk * BN + i];
+      epi_bar_sync();
+      const int x = it.x0 + row % P.BW, y = it.y0 + row / P.BW;
+      const bool valid = x < P.W && y < P.H;
+      const size_t pix = (size_t)y * P.W + x;
+      mbar_wait(tmem_full, tphase);
+      tcgen05_fence_after();
+      if (EPI == EPI_STORE_RELU || EPI == EPI_STORE) {
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+          const int img = acc ? it.img1 : it.img0;
+          __nv_bfloat16* dst = P.out + (((size_t)img * P.H * P.W + pix) * P.Cout + (size_t)it.chunk * BN);
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + acc * BN + c0, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = v[2 * j] + s_bias[c0 + 2 * j], b = v[2 * j + 1] + s_bias[c0 + 2 * j + 1];
+              if (EPI == EPI_STORE_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            if (valid) {
+              uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) d4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+        }
+      } else if (EPI == EPI_COSINE) {
+        // acc0 = image b of Concat_0(conv_feat, warp_feat) = current-frame embedding, acc1 = warped one (SYM:133-138)
+        float scc = 0.f, sww = 0.f, swc = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float ec[32], ewp[32];
+          tmem_ld32(taddr + c0, ec);
+          tmem_ld32(taddr + BN + c0, ewp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b = s_bias[c0 + j];
+            const float c = ec[j] + b, w = ewp[j] + b;
+            scc = fmaf(c, c, scc);
+            sww = fmaf(w, w, sww);
+            swc = fmaf(w, c, swc);
+          }
+        }
+        if (valid) {
+          const size_t NP = (size_t)(P.NB / 2) * P.H * P.W;
+          float* dst = P.partial + (size_t)it.chunk * 3 * NP + (size_t)it.img0 * P.H * P.W + pix;
+          dst[0] = scc;
+          dst[NP] = sww;
+          dst[2 * NP] = swc;
+        }
+      } else {   // EPI_NQ
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+          float q[NQ_MID];
+#pragma unroll
+          for (int j = 0; j < NQ_MID; ++j) q[j] = s_nq[j];                 // Nq_conv2 bias
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + acc * BN + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float a = fmaxf(v[c] + s_bias[c0 + c], 0.f);           // Nq_conv1 bias + ReLU (SYM:97-98)
+              const float4* wr = reinterpret_cast<const float4*>(s_w2t + (c0 + c) * NQ_MID);
+#pragma unroll
+              for (int j4 = 0; j4 < NQ_MID / 4; ++j4) {
+                const float4 w = wr[j4];
+                q[4 * j4 + 0] = fmaf(w.x, a, q[4 * j4 + 0]);
+                q[4 * j4 + 1] = fmaf(w.y, a, q[4 * j4 + 1]);
+                q[4 * j4 + 2] = fmaf(w.z, a, q[4 * j4 + 2]);
+                q[4 * j4 + 3] = fmaf(w.w, a, q[4 * j4 + 3]);
+              }
+            }
+          }
+          float o = s_nq[2 * NQ_MID];                                      // Nq_conv3 bias
+#pragma unroll
+          for (int j = 0; j < NQ_MID; ++j) o = fmaf(s_nq[NQ_MID + j], fmaxf(q[j], 0.f), o);   // ReLU (SYM:100), Nq_conv3
+          // image b of Concat_0(warp, conv) is the warped feature -> logits[:,0]; image b + N the current one -> [:,1]
+          if (valid) P.logits[((size_t)it.img0 * 2 + acc) * P.H * P.W + pix] = o;
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty);
+      tphase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// cosine logits from the per-chunk partial sums (fixed summation order: deterministic).  compute_weight SYM:111-116 with
+// MXNet's L2Normalization(mode='channel'): e / sqrt(sum e^2 + 1e-10);  logits[n,0] = <e_warp^, e_cur^>, [n,1] = <e_cur^, e_cur^>
+__global__ void cosine_from_partials_kernel(const float* __restrict__ partial, float* __restrict__ logits, int n_chunks, int N,
+                                            int HW) {
+  const size_t NP = (size_t)N * HW;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP) return;
+  float scc = 0.f, sww = 0.f, swc = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const float* p = partial + (size_t)c * 3 * NP + i;
+    scc += p[0];
+    sww += p[NP];
+    swc += p[2 * NP];
+  }
+  const float nc = sqrtf(scc + 1e-10f), nw = sqrtf(sww + 1e-10f);
+  const size_t n = i / HW, p = i % HW;
+  logits[(n * 2 + 0) * HW + p] = swc / (nw * nc);
+  logits[(n * 2 + 1) * HW + p] = scc / (nc * nc);
+}
+
+// (Cout,Cin,kh,kw) fp32 (MXNet's layout) -> (Cout, kh*kw*Cin) bf16: K index = tap * Cin + cin, tap = ky*kw + kx
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int kk) {
+  const size_t total = (size_t)Cout * Cin * kk;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cin = (int)(i % Cin);
+    const size_t r = i / Cin;
+    const int tap = (int)(r % kk);
+    const size_t co = r / kk;
+    out[i] = __float2bfloat16_rn(w[(co * Cin + cin) * kk + tap]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+void pick_tile(int H, int W, int* BW, int* BH) {
+  long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    const int bh = BM / bw;
+    const long cost = (long)((W + bw - 1) / bw) * bw * ((H + bh - 1) / bh) * bh;
+    if (best < 0 || cost < best) { best = cost; *BW = bw; *BH = bh; }
+  }
+}
+
+static const char* make_maps(const void* x, const void* w, const ConvParams& P, CUtensorMap* tmA, CUtensorMap* tmB) {
+  auto enc = encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled not available from the driver";
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)P.Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.NB};
+    cuuint64_t strides[3] = {(cuuint64_t)P.Cin * 2, (cuuint64_t)P.W * P.Cin * 2, (cuuint64_t)P.H * P.W * P.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the activation tensor";
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)P.taps * P.Cin, (cuuint64_t)P.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)P.taps * P.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed for the weight tensor";
+  }
+  return nullptr;
+}
+
+template <int EPI>
+static const char* launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& P, int sms, cudaStream_t stream) {
+  static bool attr_set = false;    // benign race: the attribute is idempotent
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
+    attr_set = true;
+  }
+  const int grid = P.num_items < sms ? P.num_items : sms;
+  conv_gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);
+  return nullptr;
+}
+
+const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int sms, cudaStream_t stream) {
+  if (P.NB <= 0 || (P.NB & 1)) return "the tensor-core convolutions work on image pairs (Concat_0 of two N-batches): NB must be even";
+  if (P.Cin % BK) return "Cin must be a multiple of 64";
+  if (P.Cout % BN) return "Cout must be a multiple of 256";
+  if (P.taps != 1 && P.taps != 9) return "kernel must be 1x1 or 3x3";
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) return "activation / weight pointers must be 16-byte aligned";
+  pick_tile(P.H, P.W, &P.BW, &P.BH);
+  P.tiles_x = (P.W + P.BW - 1) / P.BW;
+  P.tiles_y = (P.H + P.BH - 1) / P.BH;
+  P.n_chunks = P.Cout / BN;
+  P.kc_per_tap = P.Cin / BK;
+  P.k_steps = P.taps * P.kc_per_tap;
+  P.num_items = (P.NB / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
+  CUtensorMap tmA, tmB;
+  if (const char* e = make_maps(x, w, P, &tmA, &tmB)) return e;
+  switch (epi) {
+    case EPI_STORE_RELU: return launch_epi<EPI_STORE_RELU>(tmA, tmB, P, sms, stream);
+    case EPI_STORE: return launch_epi<EPI_STORE>(tmA, tmB, P, sms, stream);
+    case EPI_COSINE: return launch_epi<EPI_COSINE>(tmA, tmB, P, sms, stream);
+    case EPI_NQ:
+      if (P.Cout != BN) return "Nq_conv1 must have exactly 256 filters (SYM:97)";
+      return launch_epi<EPI_NQ>(tmA, tmB, P, sms, stream);
+  }
+  return "unknown epilogue";
+}
+
+void launch_cosine_finalize(const float* partial, float* logits, int n_chunks, int N, int HW, cudaStream_t stream) {
+  const size_t NP = (size_t)N * HW;
+  cosine_from_partials_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, stream>>>(partial, logits, n_chunks, N, HW);
+}
+
+void launch_pack_weight(const float* w, void* out, int Cout, int Cin, int kk, cudaStream_t stream) {
+  const size_t total = (size_t)Cout * Cin * kk;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_conv_weight_kernel<<<grid, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), Cout, Cin, kk);
+}
+
+}  // namespace tc
+}  // namespace lsfa

@@ -59,8 +59,24 @@ def nq_net(x: torch.Tensor, w1, b1, w2, b2, w3, b3) -> torch.Tensor:
     return F.conv2d(x, w3, b3)
 
 
+def pack_embed_params(embed_params):
+    """(w1,b1,w2,b2,w3,b3) as MXNet holds them -> the tensor-core kernels' form (bf16 K-major weights, f32 biases)."""
+    w1, b1, w2, b2, w3, b3 = embed_params
+    return (ops.pack_conv_weight(w1), b1.contiguous(), ops.pack_conv_weight(w2), b2.contiguous(), ops.pack_conv_weight(w3),
+            b3.contiguous())
+
+
+def pack_nq_params(nq_params):
+    w1, b1, w2, b2, w3, b3 = nq_params
+    return (ops.pack_conv_weight(w1), b1.contiguous(), w2.contiguous(), b2.contiguous(), w3.contiguous(), b3.contiguous())
+
+
+def _tc_supported(c_in, *c_outs):
+    return c_in % 64 == 0 and all(c % 256 == 0 for c in c_outs)
+
+
 def key_frame_fgfa(feat_key_old, flow, scale_map, conv_feat, embed_params, is_first_frame=None,
-                   flow_kind="flow", conv_dtype=None, **kw) -> torch.Tensor:
+                   flow_kind="flow", conv_dtype=None, packed=None, **kw) -> torch.Tensor:
     """get_key_test_symbol with add_Fgfa_net (SYM:468-470,473-474,477), exact two-phase form.
 
     ``conv_dtype=torch.bfloat16`` runs the library convolutions on cuDNN's bf16 channels-last (tensor-core) path:
@@ -74,6 +90,11 @@ def key_frame_fgfa(feat_key_old, flow, scale_map, conv_feat, embed_params, is_fi
         emb = embed_net(torch.cat([conv_feat, warp], dim=0), *embed_params)                                # SYM:133-134
         emb_cur, emb_warp = emb[:n].contiguous(), emb[n:].contiguous()                                     # SYM:135
         logits = ops.cosine_logits(emb_warp, emb_cur)                                                      # SYM:137-139
+    elif conv_dtype == "tc":
+        # this package's tcgen05 implicit-GEMM convolutions; compute_weight's reductions are em_conv3's epilogue, so the
+        # 2048-channel embeddings are never written (packed = pack_embed_params(embed_params), once per parameter set)
+        x = _lowp_input([conv_feat, warp], torch.bfloat16).permute(0, 2, 3, 1)
+        logits = ops.embed_cosine_logits(x, packed if packed is not None else pack_embed_params(embed_params))
     else:
         emb = embed_net(_lowp_input([conv_feat, warp], conv_dtype), *prepare_params(embed_params, conv_dtype))
         emb = emb.permute(0, 2, 3, 1)                                    # (2N,H,W,E) view of the channels-last result
@@ -87,10 +108,14 @@ def key_frame_fgfa(feat_key_old, flow, scale_map, conv_feat, embed_params, is_fi
 
 
 def key_frame_nq(feat_key_old, flow, scale_map, conv_feat, nq_params, is_first_frame=None,
-                 flow_kind="flow", conv_dtype=None, **kw) -> torch.Tensor:
+                 flow_kind="flow", conv_dtype=None, packed=None, **kw) -> torch.Tensor:
     """get_key_test_symbol with add_Nq_net (shipped, SYM:468-472,477).  ``conv_dtype``: see key_frame_fgfa."""
     warp = ops.warp_scale_aggregate(feat_key_old, flow, scale_map=scale_map, flow_kind=flow_kind, **kw)      # K1
     n = conv_feat.shape[0]
+    if conv_dtype == "tc":
+        x = _lowp_input([warp, conv_feat], torch.bfloat16).permute(0, 2, 3, 1)
+        logits = ops.nq_logits(x, packed if packed is not None else pack_nq_params(nq_params))             # SYM:95-101, one launch
+        return ops.blend_logits(warp, conv_feat, logits, bypass=is_first_frame)
     if conv_dtype is None or conv_dtype == torch.float32:
         q = nq_net(torch.cat([warp, conv_feat], dim=0), *nq_params)                                        # SYM:95-101
     else:

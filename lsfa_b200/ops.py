@@ -635,3 +635,93 @@ def to_nchw(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
     A.check(A.load().lsfa_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), N, Cc, H, W, lay, _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# the embedding / quality networks on tensor cores (csrc/conv_gemm_tc.cu)
+# ------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """MXNet's (Cout,Cin,k,k) float32 convolution weight -> (Cout, k*k*Cin) bf16 (K index = tap*Cin + cin), once per
+    parameter set."""
+    _dev(w, "w", torch.float32)
+    if w.dim() != 4 or w.shape[2] != w.shape[3] or w.shape[2] not in (1, 3):
+        raise ValueError("conv weight must be (Cout,Cin,k,k) with k in {1,3}, got %s" % (tuple(w.shape),))
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty((Cout, k * k * Cin), dtype=torch.bfloat16, device=w.device)
+    A.check(A.load().lsfa_pack_conv_weight_bf16(w.data_ptr(), out.data_ptr(), Cout, Cin, k, _stream()))
+    return out
+
+
+def _ksize(w_packed: torch.Tensor, Cin: int) -> int:
+    taps, rem = divmod(w_packed.shape[1], Cin)
+    if rem or taps not in (1, 9):
+        raise ValueError("packed weight (Cout, %d) does not match Cin=%d for a 1x1 or 3x3 kernel" % (w_packed.shape[1], Cin))
+    return 1 if taps == 1 else 3
+
+
+def conv_bf16_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, relu: bool = False, out=None) -> torch.Tensor:
+    """mx.sym.Convolution (stride 1, 'same' padding, with bias) [+ ReLU] on tensor cores: x (NB,H,W,Cin) bf16 channels-last,
+    w_packed from pack_conv_weight, bias (Cout,) f32 -> (NB,H,W,Cout) bf16.  NB even, Cin % 64 == 0, Cout % 256 == 0."""
+    _dev(x, "x", torch.bfloat16)
+    _dev(w_packed, "w_packed", torch.bfloat16)
+    _dev(bias, "bias", torch.float32)
+    NB, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    k = _ksize(w_packed, Cin)
+    if out is None:
+        out = torch.empty((NB, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    _dev(out, "out", torch.bfloat16)
+    A.check(A.load().lsfa_conv_bf16_nhwc(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), out.data_ptr(), NB, H, W, Cin, Cout,
+                                         k, int(bool(relu)), _stream()))
+    return out
+
+
+def embed_cosine_logits(x: torch.Tensor, packed_params, workspace=None) -> torch.Tensor:
+    """get_embednet + compute_weight of Fgfa_net (SYM:111-139) in three tensor-core launches + a tiny finalise:
+    x = Concat_0(conv_feat, warp_feat) (2N,H,W,C) bf16 channels-last; packed_params = (w1p, b1, w2p, b2, w3p, b3) with the
+    weights from pack_conv_weight -> logits (N,2,H,W) f32 ([n,0] warp vs cur, [n,1] cur vs cur).  The 2048-channel
+    embeddings are reduced in em_conv3's epilogue and never written."""
+    _dev(x, "x", torch.bfloat16)
+    w1, b1, w2, b2, w3, b3 = packed_params
+    for t, nme in ((w1, "w1"), (w2, "w2"), (w3, "w3")):
+        _dev(t, nme, torch.bfloat16)
+    for t, nme in ((b1, "b1"), (b2, "b2"), (b3, "b3")):
+        _dev(t, nme, torch.float32)
+    NB, H, W, Cc = x.shape
+    if NB % 2:
+        raise ValueError("x must hold Concat_0(conv_feat, warp_feat): an even number of images")
+    N = NB // 2
+    C1, C2, E = w1.shape[0], w2.shape[0], w3.shape[0]
+    if w1.shape[1] != Cc or w2.shape[1] != 9 * C1 or w3.shape[1] != C2:
+        raise ValueError("embedding weights do not chain: %s %s %s for C=%d" % (tuple(w1.shape), tuple(w2.shape), tuple(w3.shape), Cc))
+    lib = A.load()
+    need = lib.lsfa_embed_cosine_logits_workspace_bytes(N, H, W, C1, C2, E)
+    if workspace is None:
+        workspace = torch.empty(need + 256, dtype=torch.uint8, device=x.device)
+    off = (-workspace.data_ptr()) % 256
+    logits = torch.empty((N, 2, H, W), dtype=torch.float32, device=x.device)
+    A.check(lib.lsfa_embed_cosine_logits_bf16_nhwc(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                                   w3.data_ptr(), b3.data_ptr(), logits.data_ptr(), N, H, W, Cc, C1, C2, E,
+                                                   workspace.data_ptr() + off, workspace.numel() - off, _stream()))
+    return logits
+
+
+def nq_logits(x: torch.Tensor, packed_params) -> torch.Tensor:
+    """The convolutions of Nq_net (SYM:95-101) in one tensor-core launch: x = Concat_0(warp_feat, conv_feat) (2N,H,W,C) bf16
+    channels-last; packed_params = (w1p, b1, w2, b2, w3, b3): w1p = pack_conv_weight(Nq_conv1), the rest float32 as MXNet holds
+    them ((16,256,1,1), (16,), (1,16,1,1), (1,)) -> logits (N,2,H,W) f32 ([n,0] warp, [n,1] current)."""
+    _dev(x, "x", torch.bfloat16)
+    w1, b1, w2, b2, w3, b3 = packed_params
+    _dev(w1, "w1", torch.bfloat16)
+    for t, nme in ((b1, "b1"), (w2, "w2"), (b2, "b2"), (w3, "w3"), (b3, "b3")):
+        _dev(t, nme, torch.float32)
+    NB, H, W, Cc = x.shape
+    if NB % 2:
+        raise ValueError("x must hold Concat_0(warp_feat, conv_feat): an even number of images")
+    if w1.shape[0] != 256 or w1.shape[1] != 9 * Cc or w2.numel() != 16 * 256 or b2.numel() != 16 or w3.numel() != 16 or b3.numel() != 1:
+        raise ValueError("Nq_net parameters must be 3x3 C->256, 1x1 256->16, 1x1 16->1 (SYM:97-101)")
+    N = NB // 2
+    logits = torch.empty((N, 2, H, W), dtype=torch.float32, device=x.device)
+    A.check(A.load().lsfa_nq_logits_bf16_nhwc(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                              w3.data_ptr(), b3.data_ptr(), logits.data_ptr(), N, H, W, Cc, _stream()))
+    return logits

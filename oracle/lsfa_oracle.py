@@ -621,6 +621,35 @@ def key_frame_nq_full(feat_key_old, flow, scale_map, conv_feat, nq_params, is_fi
 
 
 # --------------------------------------------------------------------------------------
+# Stated-tolerance bf16 variant of the two networks (the tensor-core kernels of SURVEY 8f rank 2):
+# same graphs as embed_net / nq_net above with the product's rounding points made explicit -
+# inputs, convolution weights and the two hidden activations of the embedding net are rounded to
+# bf16; every accumulation, the biases, the Nq tail and compute_weight stay float32/float64.
+# --------------------------------------------------------------------------------------
+def embed_cosine_logits_bf16(x, w1, b1, w2, b2, w3, b3):
+    """x = Concat_0(conv_feat, warp_feat) (2N,C,H,W) -> logits (N,2,H,W): [n,0] = <e_warp^, e_cur^>, [n,1] = <e_cur^, e_cur^>
+    (get_embednet SYM:118-130, compute_weight SYM:111-116, Fgfa_net SYM:133-139)."""
+    r = bf16_round
+    n = x.shape[0] // 2
+    h1 = r(np.maximum(conv2d(r(x), r(w1), b1), 0))
+    h2 = r(np.maximum(conv2d(h1, r(w2), b2, pad=1), 0))
+    e = conv2d(h2, r(w3), b3)
+    l1 = cosine_weight(e[n:], e[:n])
+    l2 = cosine_weight(e[:n], e[:n])
+    return np.concatenate([l1, l2], axis=1).astype(F32)
+
+
+def nq_logits_bf16(x, w1, b1, w2, b2, w3, b3):
+    """x = Concat_0(warp_feat, conv_feat) (2N,C,H,W) -> logits (N,2,H,W): [n,0] warp, [n,1] current (Nq_net SYM:95-101)."""
+    r = bf16_round
+    n = x.shape[0] // 2
+    q = np.maximum(conv2d(r(x), r(w1), b1, pad=1), 0)
+    q = np.maximum(conv2d(q, w2, b2), 0)
+    q = conv2d(q, w3, b3)
+    return np.concatenate([q[:n], q[n:]], axis=1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
 # Algorithmic bytes (SURVEY.md section 8d) - used by bench.py and DESIGN.md
 # --------------------------------------------------------------------------------------
 def algorithmic_bytes_per_frame(C, H, W, feat_bytes=4, variant="V2", E=2048):

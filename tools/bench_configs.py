@@ -21,6 +21,13 @@ def peak():
         return 6650.0
 
 
+def tflops_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0
+
+
 def time_ms(fn, warmup=5, steps=30):
     for _ in range(warmup):
         fn()
@@ -302,6 +309,26 @@ def keyframe_rows(dev, pk, quick):
         time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nq), 2, 5), pk)
     row("key frame: Nq graph end to end (K1 + bf16 channels-last convs + blend)", N, 0,
         time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nqb, conv_dtype=torch.bfloat16), 2, 5), pk)
+    # ---- this package's tcgen05 convolutions (csrc/conv_gemm_tc.cu): same operands, same box ----
+    tf_peak = tflops_peak()
+    xb = x2b.permute(0, 2, 3, 1)                       # the contiguous (2N,H,W,C) bf16 buffer
+    pe = graphs.pack_embed_params(emb)
+    pq = graphs.pack_nq_params(nq)
+    xq = graphs._lowp_input([warp, d["cur"]], torch.bfloat16).permute(0, 2, 3, 1)
+    h1 = torch.empty((2 * N, H, W, 512), dtype=torch.bfloat16, device=dev)
+    h2 = torch.empty_like(h1)
+    for name, fn, gf in (
+            ("em_conv1 1x1 1024->512 +ReLU", lambda: ops.conv_bf16_nhwc(xb, pe[0], pe[1], relu=True, out=h1), 2 * N * 2 * HW * C * 512 / 1e9),
+            ("em_conv2 3x3 512->512 +ReLU", lambda: ops.conv_bf16_nhwc(h1, pe[2], pe[3], relu=True, out=h2), 2 * N * 2 * HW * 9 * 512 * 512 / 1e9),
+            ("embedding net + cosine logits (em_conv1,2,3 + compute_weight fused)", lambda: ops.embed_cosine_logits(xb, pe), gflop_emb),
+            ("Nq net -> logits (Nq_conv1 + fused 256->16->1 tail)", lambda: ops.nq_logits(xq, pq), gflop_nq)):
+        ms = time_ms(fn, 3, 10)
+        r = row("key frame tcgen05: %s (%.0f GFLOP = %.0f TFLOP/s = %.2f of the sustained bf16 peak %.0f)" % (
+            name, gf, gf / ms, gf / ms / tf_peak, tf_peak), N, 0, ms, pk, "hand-written tcgen05 implicit GEMM")
+    row("key frame: Fgfa graph end to end (K1 + tcgen05 convs with fused cosine + blend)", N, 0,
+        time_ms(lambda: graphs.key_frame_fgfa(d["key"], flow, d["scale_map"], d["cur"], emb, conv_dtype="tc", packed=pe), 2, 5), pk)
+    row("key frame: Nq graph end to end (K1 + tcgen05 convs + blend)", N, 0,
+        time_ms(lambda: graphs.key_frame_nq(d["key"], flow, d["scale_map"], d["cur"], nq, conv_dtype="tc", packed=pq), 2, 5), pk)
 
 
 def main():

@@ -53,7 +53,7 @@ _SEED = {"blocks": 1, "integer": 2, "half": 3, "outside": 4, "subpixel": 5}
 
 def flows(rng, N, H, W, kind):
     if kind == "blocks":         # SURVEY 8d synthetic macroblock motion, accumulated-GOP magnitude
-        return O.mv_pool(O.synth_raw_mv(rng, N, 16 * H, 16 * W, 96))
+        return np.ascontiguousarray(O.mv_pool(O.synth_raw_mv(rng, N, 16 * H, 16 * W, 96)))
     if kind == "integer":
         return rng.integers(-3, 4, size=(N, 2, H, W)).astype(np.float32)
     if kind == "half":
@@ -105,7 +105,7 @@ def test_backward_equals_cudnn_spatial_tf_sampler_backward(ops, cuda, kind, N, C
     og = torch.from_numpy(rng.standard_normal((N, C, H, W), dtype=np.float32)).to(cuda)
     out = cudnn_sampler(data, grid)
     out.backward(og)
-    for kernel in ("gather", "scatter"):
+    for kernel in (("gather", "scatter") if H * W <= 4320 else ("auto", "scatter")):   # gather: planes of <= 4,320 pixels
         gd, gg = ops.BilinearSampler_backward(data.detach(), grid.detach(), og, kernel=kernel)
         s_d = float(data.grad.abs().max())
         s_g = float(grid.grad.abs().max())

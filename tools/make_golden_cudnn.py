@@ -16,11 +16,11 @@ from oracle import lsfa_oracle as O  # noqa: E402  (input synthesis + GridGenera
 dev = torch.device("cuda", 0)
 out = {}
 rng = np.random.default_rng(7)
-cases = [("blocks", 2, 24, 38, 63), ("half", 1, 8, 17, 23), ("outside", 2, 6, 12, 20), ("subpixel", 1, 16, 68, 120)]
+cases = [("blocks", 2, 8, 38, 63), ("half", 1, 8, 17, 23), ("outside", 2, 6, 12, 20), ("subpixel", 1, 4, 68, 120)]
 for i, (kind, N, C, H, W) in enumerate(cases):
     data = O.synth_features(rng, (N, C, H, W))
     if kind == "blocks":
-        flow = O.mv_pool(O.synth_raw_mv(rng, N, 16 * H, 16 * W, 96))
+        flow = np.ascontiguousarray(O.mv_pool(O.synth_raw_mv(rng, N, 16 * H, 16 * W, 96)))
     elif kind == "half":
         flow = (rng.integers(-6, 7, size=(N, 2, H, W)) * 0.5).astype(np.float32)
     elif kind == "outside":
@@ -34,7 +34,7 @@ for i, (kind, N, C, H, W) in enumerate(cases):
     y = torch.cudnn_grid_sampler(d, g.permute(0, 2, 3, 1).contiguous())
     y.backward(torch.from_numpy(og).to(dev))
     out["c%d_kind" % i] = np.array(kind)
-    out["c%d_data" % i] = data.astype(np.float16) if False else data
+    out["c%d_data" % i] = data
     out["c%d_flow" % i] = flow
     out["c%d_og" % i] = og
     out["c%d_out" % i] = y.detach().cpu().numpy()

@@ -193,11 +193,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(FRAMES_PER_GPU, args.gpus),
-                       note="each reference step is a bounded sample of %d frames of the workload" % sample),
+        "config": workload_config(FRAMES_PER_GPU, args.gpus),      # the same dict as our arm's: same workload
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d frames x %d steps of the same workload; C port of the MXNet CPU operators "
-                                   "(GridGenerator, BilinearSampler, mul, softmax, tile, mul, add), OpenMP" % (sample, args.steps)},
+                         "sample": "each reference step is a bounded sample of %d frames of the workload, x %d steps; C port of "
+                                   "the MXNet CPU operators (GridGenerator, BilinearSampler, mul, softmax, tile, mul, add), "
+                                   "OpenMP" % (sample, args.steps)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -218,14 +218,54 @@ def measured_hbm_peak():
 
 
 def recorded_traffic(frames):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (a RECORDED figure: a
+    profiler cannot run inside the timed bench).  Returns (bytes per launch, pre-pass microseconds, source)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        per_frame = t["agg_nchw_tma_kernel"]["dram_bytes_per_frame"]
-        return float(per_frame) * frames
+        k = t["agg_nchw_tma_kernel"]
+        return float(k["dram_bytes_per_frame"]) * frames, k.get("prepass_us"), \
+            "recorded: profiles/ncu_traffic.json (%s)" % k.get("source", "ncu --set full of this kernel on this workload")
     except Exception:
-        return None
+        return None, None, "unavailable"
+
+
+def measure_pinned_copy_peak(dev, world, barrier, gather, mb=192, reps=6):
+    """GB/s of plain pinned-memory copies on every rank at once (whole-job aggregate, max time over ranks):
+    H2D alone, D2H alone, and both directions concurrently with 3 bytes in per byte out (the e2e workload's ratio)."""
+    import torch
+    n = mb << 20
+    h_in, h_out = torch.empty(3 * n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(3 * n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    cur = torch.cuda.current_stream()
+
+    def run(do_in, do_out):
+        for it in range(2):                       # pass 0 warms up, pass 1 is timed
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            s1.wait_event(e0)
+            s2.wait_event(e0)
+            for _ in range(reps):
+                if do_in:
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(h_in, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+            cur.wait_stream(s1)
+            cur.wait_stream(s2)
+            e1.record(cur)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        nbytes = reps * ((3 * n if do_in else 0) + (n if do_out else 0))
+        tot, max_ms = gather(nbytes, ms)
+        return tot / (max_ms / 1e3) / 1e9
+
+    out = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "mix_gbs": run(True, True)}
+    del h_in, h_out, d_in, d_out
+    return out
 
 
 def run_ours(args):
@@ -290,10 +330,13 @@ def run_ours(args):
     alg_bytes = algorithmic_bytes_v2(frames)
     launch_ms = ms_local / K
     achieved = alg_bytes / (launch_ms / 1e3) / 1e9
+    traffic, prepass_us, traffic_src = recorded_traffic(frames)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(frames), "kernel": "agg_nchw_tma_kernel<K=2,PPT=5,ScaleCur>",
-                "note": "launch_ms is one whole step = agg_records_kernel (index-math pre-pass, ~3 us) + the dominant "
-                        "streaming kernel, so `achieved` slightly understates the dominant kernel on its own. `peak` is "
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "agg_nchw_tma_kernel<K=2,PPT=5,ScaleCur>",
+                "prepass_us_recorded": prepass_us,
+                "note": "launch_ms is one whole step = agg_records_kernel (index-math pre-pass: 11-12 us in the ncu launch "
+                        "list under profiles/, ~3 % of the step) + the dominant streaming kernel, so `achieved` understates "
+                        "the dominant kernel on its own by that share. `peak` is "
                         "the driver-measured torch copy bandwidth (MEASURED_PEAKS.json: b.copy_(a), 1 Gi bf16), not the "
                         "hardware limit: a TMA-in/TMA-out kernel whose traffic is 3/4 reads can exceed it (frac > 1); "
                         "frac_of_nominal_8TBs and ncu's dram__throughput (profiles/) are the conservative views",
@@ -301,37 +344,71 @@ def run_ours(args):
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---------------- e2e: host buffers in, host buffer out, copies inside the timed region ----
+    # (a) what the box can move: a plain pinned cudaMemcpyAsync loop on ALL ranks at once, H2D and D2H concurrently in the
+    #     workload's own byte ratio - the denominator of e2e.roofline
+    copy_peak = measure_pinned_copy_peak(dev, world, barrier, gather_frame_counts)
+    # (b) the reference-facing call: one C-ABI lsfa_host_aggregate_f32_nchw per 64-frame batch (lsfa_b200.host.HostAggregator)
     agg = HostAggregator(frames, C, H, W, (MV_H, MV_W), dev, chunk=args.chunk, depth=3)
     out_host = torch.empty((frames, C, H, W), dtype=torch.float32).pin_memory()
     e2e_steps = K if args.e2e_steps <= 0 else args.e2e_steps
-    for _ in range(3):
-        agg(host, out_host)
-    agg.synchronize()
-    barrier()
-    agg.launches = 0
-    cur_stream = torch.cuda.current_stream()
-    pipe_streams = (agg.s_in, agg.s_run, agg.s_out)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(cur_stream)
-    for s_ in pipe_streams:
-        s_.wait_event(f0)                 # the pipeline starts after the start mark ...
-    for _ in range(e2e_steps):
-        agg(host, out_host)
-    for s_ in pipe_streams:
-        cur_stream.wait_stream(s_)        # ... and the stop mark waits for every copy and kernel
-    f1.record(cur_stream)
-    agg.synchronize()
-    torch.cuda.synchronize()
-    e2e_ms_local = f0.elapsed_time(f1)
-    barrier()
-    e2e_frames, e2e_ms = gather_frame_counts(frames * e2e_steps, e2e_ms_local)
+
+    def time_host_path(agg_, host_, steps):
+        for _ in range(3):
+            agg_(host_, out_host)
+        agg_.synchronize()
+        barrier()
+        agg_.launches = 0
+        cur_stream = torch.cuda.current_stream()
+        pipe_streams = (agg_.s_in, agg_.s_run, agg_.s_out)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(cur_stream)
+        for s_ in pipe_streams:
+            s_.wait_event(f0)                 # the pipeline starts after the start mark ...
+        for _ in range(steps):
+            agg_(host_, out_host)
+        for s_ in pipe_streams:
+            cur_stream.wait_stream(s_)        # ... and the stop mark waits for every copy and kernel
+        f1.record(cur_stream)
+        agg_.synchronize()
+        torch.cuda.synchronize()
+        ms_l = f0.elapsed_time(f1)
+        barrier()
+        return gather_frame_counts(frames * steps, ms_l)
+
+    e2e_frames, e2e_ms = time_host_path(agg, host, e2e_steps)
     bi, bo = agg.bytes_per_call()
+    e2e_gbs = world * (bi + bo) * e2e_steps / (e2e_ms / 1e3) / 1e9
     e2e = {"value": e2e_frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
            "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "launches_per_step": agg.launches // max(1, e2e_steps),
            "host_numa_binding_rank0": numa,
-           "api": "lsfa_b200.host.HostAggregator (pinned host in/out, %d-frame chunks, 3-stream pipeline; of each "
-                  "600x1000 MV field only the 2 rows in 16 the reference's stride-16 resize reads cross PCIe)" % agg.chunk}
-    checksum = float(out_host[0, 0, 0, :8].sum())    # the result really is on the host
+           "roofline": {"bound": "pcie", "achieved": e2e_gbs, "peak": copy_peak["mix_gbs"], "unit": "GB/s",
+                        "frac": e2e_gbs / copy_peak["mix_gbs"] if copy_peak["mix_gbs"] else None,
+                        "peak_source": "measured in this run: pinned cudaMemcpyAsync loop, H2D and D2H concurrently (3:1 bytes, "
+                                       "the workload's ratio) on all %d rank(s) at once, whole-job GB/s" % world,
+                        "h2d_only_gbs": copy_peak["h2d_gbs"], "d2h_only_gbs": copy_peak["d2h_gbs"]},
+           "api": "lsfa_host_aggregate_f32_nchw through lsfa_b200.host.HostAggregator (one C-ABI call per batch: pinned host "
+                  "in/out, %d-frame chunks, 3-stream pipeline over caller-owned staging; of each 600x1000 MV field only the 2 "
+                  "rows in 16 the reference's stride-16 resize reads cross PCIe)" % agg.chunk}
+    checksum_src = out_host[0, 0, 0, :8].clone()
+    # (c) the reference's GOP contract (core/tester.py:246-252): key feature resident on the device, one upload per GOP of
+    #     11 non-key frames; every frame still brings its own scale map, current feature, MVs and logits and takes its output home
+    gop_len = 11
+    n_keys = (frames + gop_len - 1) // gop_len
+    agg_g = HostAggregator(frames, C, H, W, (MV_H, MV_W), dev, chunk=args.chunk, depth=3, num_slots=n_keys)
+    host_g = {k: host[k] for k in ("scale_map", "cur", "mv", "logits")}
+    host_g["key_index"] = (torch.arange(frames, dtype=torch.int32) // gop_len).pin_memory()
+    host_g["new_keys"] = host["key"][:n_keys]
+    host_g["key_slot"] = torch.arange(n_keys, dtype=torch.int32).pin_memory()
+    g_frames, g_ms = time_host_path(agg_g, host_g, e2e_steps)
+    gbi, gbo = agg_g.bytes_per_call(host_g)
+    g_gbs = world * (gbi + gbo) * e2e_steps / (g_ms / 1e3) / 1e9
+    e2e["gop_contract"] = {"value": g_frames / (g_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": gbi, "d2h_bytes_per_step": gbo,
+                           "ms_per_step": g_ms / e2e_steps, "key_uploads_per_step": n_keys, "gop_len": gop_len,
+                           "achieved_gbs": g_gbs, "frac_of_measured_copy_peak": g_gbs / copy_peak["mix_gbs"] if copy_peak["mix_gbs"] else None,
+                           "note": "second row, not the headline: the key feature stays in a device table across its GOP "
+                                   "(core/tester.py:246-252), frames name their slot through key_index"}
+    del agg_g
+    checksum = float(checksum_src.sum())    # the result really is on the host
     try:
         os.sched_setaffinity(0, affinity0)           # the CPU baseline below gets every host core back
     except OSError:
@@ -342,12 +419,11 @@ def run_ours(args):
         extra = run_extras(dev, d, args)
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         try:
-            t_probe = time.perf_counter()
             fps1, cores, _ = cpu_reference_fps(8, reps=1, warmup=1)
-            probe = time.perf_counter() - t_probe
-            reps = int(max(2, min(800, 15.0 / max(8 / fps1, 1e-3))))     # ~15 s of CPU work
+            budget = 15.0 if world == 1 else 4.0      # N > 1: a short sample, the other ranks wait at the final barrier
+            reps = int(max(2, min(800, budget / max(8 / fps1, 1e-3))))     # ~15 s of CPU work
             fps, cores, _ = cpu_reference_fps(8, reps=reps, warmup=0)
             cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "8 frames x %d repetitions (~%.0f s) of the same workload; C port of the MXNet "
@@ -447,7 +523,175 @@ def run_extras(dev, d, args):
                                   "frac_of_measured_peak": gb / peak}
     except Exception as e:
         out["fused_bf16_nhwc"] = {"error": repr(e)}
+    for name, fn in (("cfg1_single_frame", extra_cfg1), ("cfg4_hires_68x120", extra_cfg4), ("cfg5_multi_stream", extra_cfg5),
+                     ("keyframe_networks_tcgen05", extra_keyframe)):
+        torch.cuda.empty_cache()
+        try:
+            out[name] = fn(dev, d, peak, steps)
+        except Exception as e:
+            out[name] = {"error": repr(e)}
     return out
+
+
+def extra_cfg1(dev, d, peak, steps):
+    """BASELINE configs[0]: ONE non-key frame, 1024x38x63 fp32 + a 600x1000 MV field, GridGenerator(warp) + BilinearSampler:
+    latency of the three drop-in operators and of the fused op (eager and replayed from a CUDA graph), with the stronger
+    CPU baseline SURVEY 8d names beside it: torch.nn.functional.grid_sample on the host's cores."""
+    import torch
+
+    from lsfa_b200 import ops
+    F4, HW = C * H * W * 4, H * W
+    key, mv = d["key"][:1].contiguous(), d["mv"][:1].contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    grid = torch.empty((1, 2, H, W), device=dev)
+    o = torch.empty_like(key)
+    r = {}
+    ms = time_launches(lambda: ops.BilinearSampler(key, ops.GridGenerator(ops.mv_pool(mv), out=grid), out=o), 10, 200)
+    r["three_dropin_operators_us"] = 1e3 * ms
+    p0 = ops.PreparedAggregate(key, mv, flow_kind="raw")
+    ms = time_launches(lambda: p0.run(s), 10, 200)
+    r["fused_warp_us"] = 1e3 * ms
+    r["fused_warp_launches"] = p0.launches
+    p2 = ops.PreparedAggregate(key, mv, flow_kind="raw", cur=d["cur"][:1].contiguous(), scale_map=d["scale_map"][:1].contiguous(),
+                               weight_mode="logits", logits=d["logits"][:1].contiguous())
+    ms = time_launches(lambda: p2.run(s), 10, 200)
+    r["fused_v2_us"] = 1e3 * ms
+    r["fused_v2_launches"] = p2.launches
+    for tag, p in (("fused_warp_graph_us", p0), ("fused_v2_graph_us", p2)):
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                p.run(side.cuda_stream)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                p.run(side.cuda_stream)
+        r[tag] = 1e3 * time_launches(g.replay, 10, 200)
+    r["bytes_v0"] = 2 * F4 + 32 * HW
+    r["frac_of_measured_peak_fused_warp_graph"] = r["bytes_v0"] / (r["fused_warp_graph_us"] * 1e-6) / 1e9 / peak
+    # CPU side by side: torch.grid_sample (align_corners=True, zeros) = a7+a8 on the host cores
+    try:
+        nthr = len(os.sched_getaffinity(0))
+        torch.set_num_threads(nthr)
+        kc = key.cpu()
+        gc = ops.GridGenerator(ops.mv_pool(mv)).cpu().permute(0, 2, 3, 1).contiguous()
+        for _ in range(3):
+            torch.nn.functional.grid_sample(kc, gc, mode="bilinear", padding_mode="zeros", align_corners=True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            torch.nn.functional.grid_sample(kc, gc, mode="bilinear", padding_mode="zeros", align_corners=True)
+        r["cpu_torch_grid_sample_ms"] = 1e3 * (time.perf_counter() - t0) / 10
+        r["cpu_threads"] = nthr
+    except Exception as e:
+        r["cpu_torch_grid_sample_ms"] = None
+        r["cpu_error"] = repr(e)
+    return r
+
+
+def extra_cfg4(dev, d, peak, steps):
+    """BASELINE configs[3]: 1080p -> 1024x68x120 features, batch 128, fused V2 in fp32 NCHW and bf16 channels-last
+    (inputs generated on the device; 17 GB / 8.6 GB working sets)."""
+    import torch
+
+    from lsfa_b200 import ops
+    N4, H4, W4 = 128, 68, 120
+    g = torch.Generator(device=dev).manual_seed(4)
+    blk = torch.randint(-96, 97, (N4, H4, W4, 2), device=dev, generator=g, dtype=torch.int32)
+    blk[torch.rand((N4, H4, W4), device=dev, generator=g) < 0.5] = 0
+    mv = blk.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :1080, :1920].contiguous()
+    lg = torch.randn((N4, 2, H4, W4), device=dev, generator=g)
+    r = {}
+    s = torch.cuda.current_stream().cuda_stream
+    for tag, dt, lay, fb in (("fp32_nchw", torch.float32, "nchw", 4), ("bf16_nhwc", torch.bfloat16, "nhwc_bf16", 2)):
+        shape = (N4, C, H4, W4) if lay == "nchw" else (N4, H4, W4, C)
+        key = torch.randn(shape, device=dev, generator=g, dtype=torch.float32).clamp_(min=0).to(dt)
+        cur = torch.randn(shape, device=dev, generator=g, dtype=torch.float32).clamp_(min=0).to(dt)
+        sm = (1 + 0.1 * torch.randn(shape, device=dev, generator=g, dtype=torch.float32)).to(dt)
+        prep = ops.PreparedAggregate(key, mv, flow_kind="raw", cur=cur, scale_map=sm, weight_mode="logits", logits=lg, layout=lay)
+        ms = time_launches(lambda: prep.run(s), 3, min(steps, 10))
+        alg = N4 * (4 * C * H4 * W4 * fb + 40 * H4 * W4)
+        gb = alg / (ms / 1e3) / 1e9
+        r[tag] = {"frames": N4, "frames_per_s": N4 / (ms / 1e3), "ms_per_step": ms, "achieved_gbs": gb, "frac_of_measured_peak": gb / peak}
+        del key, cur, sm, prep
+        torch.cuda.empty_cache()
+    return r
+
+
+def extra_cfg5(dev, d, peak, steps):
+    """BASELINE configs[4] on this GPU: 256 independent streams x 10 non-key frames through lsfa_b200.driver.StreamScheduler
+    (one key feature per stream in a device table, frames name it through key_index; the reference's shipped non-key graph
+    SYM:570-586: warp(key, MV) + rnet_conv0(res) + current feature).  tools/bench_streams.py sweeps 64..1024 streams."""
+    import torch
+
+    from lsfa_b200 import streams
+    from lsfa_b200.driver import StreamScheduler
+    S, B = 256, 80
+    g = torch.Generator(device=dev).manual_seed(5)
+    cur = d["cur"][:min(B, d["cur"].shape[0])]
+    reps = -(-B // cur.shape[0])
+    cur = cur.repeat(reps, 1, 1, 1)[:B].contiguous()
+    mv = d["mv"].repeat(reps, 1, 1, 1)[:B].contiguous()
+    res = torch.randn((B, 3, H, W), device=dev, generator=g) * 30
+    rnet_w = 0.01 * torch.randn((C, 3), device=dev, generator=g)
+    rnet_b = torch.zeros((C,), device=dev)
+    out = torch.empty_like(cur)
+    sch = StreamScheduler([streams.KEY_FRAME_INTERVAL] * S, C, (H, W), dev)
+    sch.key_table.normal_(generator=g).clamp_(min=0)
+    batches = sch.batches(B)
+    slots = [torch.as_tensor(b[2], dtype=torch.int32, device=dev) for b in batches]
+    frames = sum(len(b[2]) for b in batches)
+
+    def step():
+        for sl in slots:
+            m = sl.numel()
+            sch.run_non_key_batch(sl, mv[:m], cur[:m], res=res[:m], rnet_w=rnet_w, rnet_b=rnet_b, out=out[:m])
+
+    ms = time_launches(step, 2, 5)
+    F4, HW = C * H * W * 4, H * W
+    alg = 2 * F4 + F4 // 10 + 44 * HW
+    fps = frames / (ms / 1e3)
+    return {"streams": S, "frames_per_step": frames, "launches_per_step": len(slots), "ms_per_step": ms, "frames_per_s": fps,
+            "alg_bytes_per_frame": alg, "achieved_gbs": fps * alg / 1e9, "frac_of_measured_peak": fps * alg / 1e9 / peak,
+            "key_table_gb": sch.key_table.numel() * 4 / 1e9}
+
+
+def extra_keyframe(dev, d, peak, steps):
+    """the embedding network + cosine logits of Fgfa_net and the Nq network (SYM:94-139) for 16 key frames at
+    1024x38x63: this package's tcgen05 implicit-GEMM kernels against cuDNN's bf16 channels-last convolutions on the same
+    operands, with the fraction of the measured sustained bf16 tensor peak."""
+    import torch
+
+    from lsfa_b200 import graphs, ops
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf_peak = float(json.load(f)["bf16_tflops_sustained"])
+        tf_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        tf_peak, tf_src = 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+    N, E = 16, 2048
+    HW = H * W
+    g = torch.Generator(device=dev).manual_seed(6)
+    rn = lambda *sh: 0.01 * torch.randn(sh, device=dev, generator=g)  # noqa: E731
+    emb = (rn(512, C, 1, 1), rn(512), rn(512, 512, 3, 3), rn(512), rn(E, 512, 1, 1), rn(E))
+    nq = (rn(256, C, 3, 3), rn(256), rn(16, 256, 1, 1), rn(16), rn(1, 16, 1, 1), rn(1))
+    x = torch.cat([d["cur"][:N], d["key"][:N]], dim=0)
+    xb = graphs._lowp_input([x], torch.bfloat16)                  # logical NCHW, channels-last bf16
+    xn = xb.permute(0, 2, 3, 1)
+    gf_emb = 2 * N * 2 * HW * (C * 512 + 9 * 512 * 512 + 512 * E) / 1e9
+    gf_nq = 2 * N * 2 * HW * (9 * C * 256 + 256 * 16 + 16) / 1e9
+    pe, pq = graphs.pack_embed_params(emb), graphs.pack_nq_params(nq)
+    embb, nqb = graphs.prepare_params(emb, torch.bfloat16), graphs.prepare_params(nq, torch.bfloat16)
+    r = {"key_frames": N, "tensor_peak_tflops": tf_peak, "tensor_peak_source": tf_src}
+    ms = time_launches(lambda: ops.embed_cosine_logits(xn, pe), 3, 10)
+    r["embed_cosine_tcgen05"] = {"ms": ms, "gflop": gf_emb, "tflops": gf_emb / ms, "frac_of_sustained_bf16_peak": gf_emb / ms / tf_peak,
+                                 "launches": 4, "writes_embeddings": False}
+    ms = time_launches(lambda: ops.nq_logits(xn, pq), 3, 10)
+    r["nq_tcgen05"] = {"ms": ms, "gflop": gf_nq, "tflops": gf_nq / ms, "frac_of_sustained_bf16_peak": gf_nq / ms / tf_peak, "launches": 1}
+    ms = time_launches(lambda: graphs.embed_net(xb, *embb), 2, 5)
+    r["embed_convs_cudnn_bf16"] = {"ms": ms, "tflops": gf_emb / ms, "note": "library arm: convolutions only, embeddings written to HBM, cosine not included"}
+    ms = time_launches(lambda: graphs.nq_net(xb, *nqb), 2, 5)
+    r["nq_convs_cudnn_bf16"] = {"ms": ms, "tflops": gf_nq / ms}
+    return r
 
 
 def main():

@@ -182,6 +182,53 @@ LSFA_API int lsfa_res_coviar_pool_i32(const int32_t* res_coviar, float* out, int
 LSFA_API int lsfa_mv_centre_rows_h2d(const void* mv_host, void* mv_dev, int N, int h, int w, size_t* bytes_out,
                             void* stream);
 
+/* ---- the reference-facing HOST path: host buffers in, host buffer out ---------------------------------------
+ * In the reference every forward is host -> device -> host: `_load_data` copies the batch to the GPU
+ * (dff_rfcn/core/DataParallelExecutorGroup.py:24-39), the executor runs, `asnumpy()` brings the result back
+ * (core/tester.py:138-145), and the key-frame feature stays ON the device between the frames of a GOP
+ * (core/tester.py:246-252).  lsfa_host_aggregate_f32_nchw is that contract for the fused operator with the copies
+ * explicit and overlapped: the N frames are cut into chunks, and three streams pipeline
+ *     H2D(chunk i+1) | fused kernel(chunk i) | D2H(chunk i-1)
+ * over `depth` staging slots.  Everything is ENQUEUED (no synchronisation): `out` is valid once stream_out has drained.
+ * All host pointers must be page-locked (cudaHostAlloc / cudaHostRegister) for the copies to be asynchronous.
+ * Of each (mv_h,mv_w,2) motion-vector image only the rows the stride-16 reduction reads cross PCIe
+ * (lsfa_mv_centre_rows_h2d).  Device memory is the caller's: `staging` (lsfa_host_aggregate_staging_bytes, 256-byte
+ * aligned, no initialisation needed, one per in-flight call sequence) and, in GOP mode, the key table.
+ *
+ * key_index == NULL  "private keys": key (N,C,H,W) holds one key feature per frame, uploaded with the frame.
+ * key_index != NULL  "GOP mode": frame n samples key_table[key_index[n]]; the num_new_keys features in `key` are first
+ *                    uploaded into slots key_slot[0..num_new_keys) of the table (the key frames that arrived with this
+ *                    batch) - a key crosses PCIe once per GOP, not once per frame.  key_index / key_slot are HOST arrays. */
+typedef struct LsfaHostAggArgs {
+  int32_t struct_bytes;          /* = sizeof(LsfaHostAggArgs) */
+  int32_t N, C, H, W;            /* frames of this call; features are NCHW float32 */
+  int32_t mv_h, mv_w;            /* per-frame raw MV image (mv_h,mv_w,2) int32 at network scale (image.py:204); H = ceil(mv_h/16) */
+  double  im_scale;              /* image.py:224: flow = pooled * im_scale / 16 */
+  int32_t weight_mode;           /* LSFA_W_NONE | LSFA_W_ADD | LSFA_W_MEAN | LSFA_W_LOGITS */
+  int32_t num_new_keys;          /* GOP mode: key features uploaded by this call (may be 0) */
+  const float*   key;            /* host: (N,C,H,W) private keys | (num_new_keys,C,H,W) in GOP mode */
+  const int32_t* key_slot;       /* host: (num_new_keys) */
+  const int32_t* key_index;      /* host: (N) or NULL */
+  const float*   scale_map;      /* host: (N,C,H,W) or NULL */
+  const float*   cur;            /* host: (N,C,H,W); NULL only for LSFA_W_NONE */
+  const int32_t* mv;             /* host: (N,mv_h,mv_w,2) */
+  const float*   logits;         /* host: (N,2,H,W) for LSFA_W_LOGITS */
+  float*         out;            /* host: (N,C,H,W) */
+  float*  key_table;             /* device: (num_slots,C,H,W), GOP mode */
+  int32_t num_slots;
+  int32_t chunk;                 /* frames per pipeline chunk (>= 1) */
+  int32_t depth;                 /* staging slots, 2..8 */
+  void*   staging;               /* device scratch */
+  size_t  staging_bytes;
+  void*   stream_in;             /* cudaStream_t of the H2D copies   */
+  void*   stream_run;            /* cudaStream_t of the fused kernel */
+  void*   stream_out;            /* cudaStream_t of the D2H copies (the three may be the same stream: no overlap) */
+} LsfaHostAggArgs;
+LSFA_API size_t lsfa_host_aggregate_staging_bytes(const LsfaHostAggArgs* args);
+LSFA_API int    lsfa_host_aggregate_f32_nchw(const LsfaHostAggArgs* args);
+/* bytes one call moves over PCIe: *h2d, *d2h (either may be NULL) */
+LSFA_API int    lsfa_host_aggregate_bytes(const LsfaHostAggArgs* args, size_t* h2d, size_t* d2h);
+
 /* a7 - mx.sym.GridGenerator(data=flow, transform_type='warp') (SYM:306,320,468,571,678).
  * flow, grid: (N,2,H,W) float32. */
 LSFA_API int lsfa_grid_generator_warp_f32(const float* flow, float* grid, int N, int H, int W,

@@ -58,6 +58,22 @@ class LsfaAggArgs(C.Structure):
     ]
 
 
+class LsfaHostAggArgs(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32),
+        ("N", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("mv_h", C.c_int32), ("mv_w", C.c_int32), ("im_scale", C.c_double),
+        ("weight_mode", C.c_int32), ("num_new_keys", C.c_int32),
+        ("key", C.c_void_p), ("key_slot", C.c_void_p), ("key_index", C.c_void_p),
+        ("scale_map", C.c_void_p), ("cur", C.c_void_p), ("mv", C.c_void_p), ("logits", C.c_void_p),
+        ("out", C.c_void_p),
+        ("key_table", C.c_void_p), ("num_slots", C.c_int32),
+        ("chunk", C.c_int32), ("depth", C.c_int32),
+        ("staging", C.c_void_p), ("staging_bytes", C.c_size_t),
+        ("stream_in", C.c_void_p), ("stream_run", C.c_void_p), ("stream_out", C.c_void_p),
+    ]
+
+
 _I, _D, _P, _SZ = C.c_int, C.c_double, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); also the list the symbol-export test checks
@@ -70,6 +86,9 @@ PROTOTYPES = {
     "lsfa_res_pool_f32": (_I, [_P, _P, _I, _I, _I, _P, _D, _I, _P]),
     "lsfa_res_coviar_pool_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _D, _I, _P, _D, _I, _P]),
     "lsfa_mv_centre_rows_h2d": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "lsfa_host_aggregate_staging_bytes": (_SZ, [C.POINTER(LsfaHostAggArgs)]),
+    "lsfa_host_aggregate_f32_nchw": (_I, [C.POINTER(LsfaHostAggArgs)]),
+    "lsfa_host_aggregate_bytes": (_I, [C.POINTER(LsfaHostAggArgs), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "lsfa_mv_prepare_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _D, _I, _I, _P]),
     "lsfa_grid_generator_warp_f32": (_I, [_P, _P, _I, _I, _I, _P]),
     "lsfa_bilinear_sampler_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -81,6 +81,21 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace lsfa {
+// for the other translation units that report through lsfa_last_error() (host_pipeline.cu)
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace lsfa
+
+namespace {
+
 int cuda_result(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return LSFA_OK;
   return fail(LSFA_E_CUDA, "%s: %s", what, cudaGetErrorString(e));

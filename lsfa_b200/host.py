@@ -11,25 +11,35 @@ Only torch memory/stream/event plumbing lives here; the arithmetic is the C-ABI 
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+import ctypes
+from typing import Dict
 
 import torch
 
 from . import _cabi as A
-from . import ops
-
-_FEATURE_KEYS = ("key", "scale_map", "cur")
 
 
 class HostAggregator:
-    """Key-frame Nq-style aggregation (warp x scale, softmax-logit blend) from host buffers.
+    """The fused operator from pinned HOST buffers to a pinned host buffer, pipelined: a thin holder of the caller-owned
+    resources (device staging, three streams, optionally the device key table) around ONE C-ABI call per batch,
+    ``lsfa_host_aggregate_f32_nchw`` (include/lsfa_ops.h; lsfa_b200/csrc/host_pipeline.cu) - the entry point a
+    reference-side binding would call in place of ``_load_data`` + forward + ``asnumpy()``.
 
-    host inputs (pinned, NCHW float32): key, scale_map, cur (N,C,H,W); mv (N,h,w,2) int32;
-    logits (N,2,H,W).  Output: pinned (N,C,H,W) float32.
+    host inputs (pinned, NCHW float32): scale_map (optional), cur (N,C,H,W); mv (N,h,w,2) int32 at network scale;
+    logits (N,2,H,W) when weight_mode='logits'.  Output: pinned (N,C,H,W) float32.
+    Keys: private (``host['key']`` (N,C,H,W), one per frame, uploaded with the frame) or - ``num_slots > 0`` - the GOP
+    contract of the reference (core/tester.py:246-252): a device key table of num_slots features;
+    ``host['key_index']`` (N,) int32 says which slot each frame samples, and ``host['new_keys']`` (K,C,H,W) +
+    ``host['key_slot']`` (K,) int32 are the key frames that arrived with this batch (uploaded once, first).
     """
 
+    MODES = {"none": A.W_NONE, "add": A.W_ADD, "mean": A.W_MEAN, "logits": A.W_LOGITS}
+
     def __init__(self, N: int, C: int, H: int, W: int, mv_hw, device, chunk: int = 8, depth: int = 2,
-                 weight_mode: str = "logits", use_scale: bool = True):
+                 weight_mode: str = "logits", use_scale: bool = True, im_scale: float = 1.0, num_slots: int = 0):
+        if weight_mode not in self.MODES:
+            raise ValueError("weight_mode must be one of %s (the host path has no embedding inputs), got %r"
+                             % (sorted(self.MODES), weight_mode))
         self.N, self.C, self.H, self.W = N, C, H, W
         self.mv_h, self.mv_w = mv_hw
         self.device = torch.device(device)
@@ -37,76 +47,106 @@ class HostAggregator:
         self.depth = depth
         self.weight_mode = weight_mode
         self.use_scale = use_scale
-        f = (self.chunk, C, H, W)
-        self.stage = []
-        for _ in range(depth):
-            buf = {k: torch.empty(f, dtype=torch.float32, device=self.device) for k in _FEATURE_KEYS}
-            buf["out"] = torch.empty(f, dtype=torch.float32, device=self.device)
-            # zeroed once: only the rows the stride-16 reduction reads are ever copied in (see __call__)
-            buf["mv"] = torch.zeros((self.chunk, self.mv_h, self.mv_w, 2), dtype=torch.int32, device=self.device)
-            buf["logits"] = torch.empty((self.chunk, 2, H, W), dtype=torch.float32, device=self.device)
-            self.stage.append(buf)
-        self.s_in = torch.cuda.Stream(self.device)
-        self.s_run = torch.cuda.Stream(self.device)
-        self.s_out = torch.cuda.Stream(self.device)
-        self.ev_in = [torch.cuda.Event() for _ in range(depth)]      # inputs of slot landed
-        self.ev_run = [torch.cuda.Event() for _ in range(depth)]     # kernel of slot done
-        self.ev_out = [torch.cuda.Event() for _ in range(depth)]     # output of slot copied out
-        self._primed = [False] * depth   # slot has been used (its events recorded) at least once
+        self.im_scale = float(im_scale)
+        self.num_slots = int(num_slots)
+        self._lib = A.load()
+        with torch.cuda.device(self.device):
+            self.s_in = torch.cuda.Stream(self.device)
+            self.s_run = torch.cuda.Stream(self.device)
+            self.s_out = torch.cuda.Stream(self.device)
+            self.key_table = (torch.empty((self.num_slots, C, H, W), dtype=torch.float32, device=self.device)
+                              if self.num_slots else None)
+            probe = self._args(None, None, sizing=True)
+            need = self._lib.lsfa_host_aggregate_staging_bytes(probe)
+            if need == 0:
+                A.check(self._lib.lsfa_host_aggregate_f32_nchw(probe))      # raises with the library's message
+            # torch.empty: nothing here is read before the pipeline has written it (no fill kernel on another stream)
+            self.staging = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        self._staging_off = (-self.staging.data_ptr()) % 256
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.launches = 0
-        self._lib = A.load()
+        self.calls = 0
+
+    # -- argument block ----------------------------------------------------------------------------------------
+    def _args(self, host, out_host, sizing=False):
+        a = A.LsfaHostAggArgs()
+        a.struct_bytes = ctypes.sizeof(A.LsfaHostAggArgs)
+        a.N, a.C, a.H, a.W = self.N, self.C, self.H, self.W
+        a.mv_h, a.mv_w, a.im_scale = self.mv_h, self.mv_w, self.im_scale
+        a.weight_mode = self.MODES[self.weight_mode]
+        a.chunk, a.depth = self.chunk, self.depth
+        a.stream_in, a.stream_run, a.stream_out = self.s_in.cuda_stream, self.s_run.cuda_stream, self.s_out.cuda_stream
+        gop = self.num_slots > 0
+        if gop:
+            a.key_table, a.num_slots = self.key_table.data_ptr(), self.num_slots
+        if sizing:      # placeholders: the size query looks at which inputs exist, never at their contents
+            z = ctypes.c_int32 * self.N
+            self._zero_index = z()
+            a.key, a.mv, a.out = 256, 256, 256
+            a.key_index = ctypes.addressof(self._zero_index) if gop else None
+            a.scale_map = 256 if self.use_scale else None
+            a.cur = 256 if self.weight_mode != "none" else None
+            a.logits = 256 if self.weight_mode == "logits" else None
+            return a
+        need = ["mv"] + (["scale_map"] if self.use_scale else []) + (["cur"] if self.weight_mode != "none" else []) \
+            + (["logits"] if self.weight_mode == "logits" else []) + (["key_index"] if gop else ["key"])
+        for k in need:
+            if k not in host:
+                raise KeyError("host[%r] is required for weight_mode=%r, use_scale=%r, %s keys"
+                               % (k, self.weight_mode, self.use_scale, "table" if gop else "private"))
+        for k, t in list(host.items()) + ([("out", out_host)] if out_host is not None else []):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError("%s must be a contiguous HOST tensor" % k)
+            if not t.is_pinned():
+                raise ValueError("%s must be pinned (page-locked) host memory for the copies to be asynchronous" % k)
+        a.mv, a.out = host["mv"].data_ptr(), (out_host.data_ptr() if out_host is not None else 256)
+        a.scale_map = host["scale_map"].data_ptr() if self.use_scale else None
+        a.cur = host["cur"].data_ptr() if self.weight_mode != "none" else None
+        a.logits = host["logits"].data_ptr() if self.weight_mode == "logits" else None
+        if gop:
+            a.key_index = host["key_index"].data_ptr()
+            nk = host["new_keys"].shape[0] if "new_keys" in host else 0
+            a.num_new_keys = nk
+            if nk:
+                a.key, a.key_slot = host["new_keys"].data_ptr(), host["key_slot"].data_ptr()
+        else:
+            a.key = host["key"].data_ptr()
+        a.staging = self.staging.data_ptr() + self._staging_off
+        a.staging_bytes = self.staging.numel() - self._staging_off
+        return a
 
     def mv_rows_copied(self) -> int:
         """Rows 16k+7 and 16k+8 below mv_h: what image.py:221 (cv2.resize fx=1/16 = the centre 2x2 of each block) reads."""
         return sum(1 for r in range(self.mv_h) if r % 16 in (7, 8))
 
-    def bytes_per_call(self):
-        per_frame_in = (3 if self.use_scale else 2) * self.C * self.H * self.W * 4 \
-            + self.mv_rows_copied() * self.mv_w * 2 * 4 + 2 * self.H * self.W * 4
-        per_frame_out = self.C * self.H * self.W * 4
-        return self.N * per_frame_in, self.N * per_frame_out
+    def bytes_per_call(self, host=None):
+        """(H2D, D2H) bytes of one call, as the library counts them.  GOP mode: pass the host dict (it depends on how
+        many key frames arrive with the batch)."""
+        if host is None and self.num_slots:
+            raise ValueError("GOP mode: pass the host dict")
+        a = self._args(None, None, sizing=True) if host is None else self._args(host, None)
+        bi, bo = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        A.check(self._lib.lsfa_host_aggregate_bytes(a, ctypes.byref(bi), ctypes.byref(bo)))
+        return bi.value, bo.value
 
     def __call__(self, host: Dict[str, torch.Tensor], out_host: torch.Tensor) -> torch.Tensor:
-        """Enqueue the whole batch; returns out_host (valid after ``self.synchronize()``)."""
+        """Enqueue the whole batch (one C-ABI call); returns out_host (valid after ``self.synchronize()``)."""
+        a = self._args(host, out_host)
+        with torch.cuda.device(self.device):
+            A.check(self._lib.lsfa_host_aggregate_f32_nchw(a))
+        bi, bo = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        A.check(self._lib.lsfa_host_aggregate_bytes(a, ctypes.byref(bi), ctypes.byref(bo)))
+        self.h2d_bytes += bi.value
+        self.d2h_bytes += bo.value
         n_chunks = (self.N + self.chunk - 1) // self.chunk
-        feats = [k for k in _FEATURE_KEYS if (k != "scale_map" or self.use_scale)]
-        for i in range(n_chunks):
-            slot = i % self.depth
-            lo, hi = i * self.chunk, min(self.N, (i + 1) * self.chunk)
-            m = hi - lo
-            buf = self.stage[slot]
-            with torch.cuda.stream(self.s_in):
-                if self._primed[slot]:
-                    self.s_in.wait_event(self.ev_run[slot])      # previous kernel on this slot has read its inputs
-                for k in feats + ["logits"]:
-                    buf[k][:m].copy_(host[k][lo:hi], non_blocking=True)
-                # motion vectors: the parity-mode reduction reads 2 rows of every 16, so only those cross PCIe
-                # (1/8 of the field: 0.6 MB instead of 4.8 MB per 600x1000 frame), into a full-size device image
-                A.check(self._lib.lsfa_mv_centre_rows_h2d(host["mv"][lo:hi].data_ptr(), buf["mv"].data_ptr(), m, self.mv_h,
-                                                          self.mv_w, None, self.s_in.cuda_stream))
-                self.ev_in[slot].record(self.s_in)
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(self.ev_in[slot])
-                if self._primed[slot]:
-                    self.s_run.wait_event(self.ev_out[slot])     # previous output of this slot has left
-                ops.warp_scale_aggregate(buf["key"][:m], buf["mv"][:m], flow_kind="raw", cur=buf["cur"][:m],
-                                         scale_map=buf["scale_map"][:m] if self.use_scale else None,
-                                         weight_mode=self.weight_mode,
-                                         logits=buf["logits"][:m] if self.weight_mode == "logits" else None,
-                                         out=buf["out"][:m])
-                self.launches += 1
-                self.ev_run[slot].record(self.s_run)
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(self.ev_run[slot])
-                out_host[lo:hi].copy_(buf["out"][:m], non_blocking=True)
-                self.ev_out[slot].record(self.s_out)
-            self._primed[slot] = True
-        bi, bo = self.bytes_per_call()
-        self.h2d_bytes += bi
-        self.d2h_bytes += bo
+        self.launches += n_chunks * self.launches_per_chunk()
+        self.calls += 1
         return out_host
+
+    def launches_per_chunk(self) -> int:
+        """Kernels the fused operator enqueues per chunk (record pre-pass + streaming kernel with the staging workspace)."""
+        return 2
 
     def synchronize(self):
         self.s_in.synchronize()

@@ -194,7 +194,6 @@ cudaError_t launch_agg_nchw_plane(const AggParams& P, size_t smem, cudaStream_t 
 // It runs just before the streaming kernel in stream order (~3 us for 64 frames).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) agg_records_kernel(const __grid_constant__ AggParams P, uint4* __restrict__ rec) {
-  pdl_launch_dependents();
   const long long total = (long long)P.N * P.HW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -288,6 +287,8 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     // stages hold key planes only.  LSFA_TMA_STAGED_STORE=1 keeps the staged form (ablation).
     const bool direct = var == kVarWarpOnly && getenv("LSFA_TMA_STAGED_STORE") == nullptr;
     const unsigned stage_bytes = direct ? off_scale : off_io + (io_bytes + 127u) / 128u * 128u;
+    // (variants WITH a current feature keep the staged store: direct stores measured 168.2k -> 167.4k frames/s on the
+    // headline and 167k -> 133k on the shared-key stream sweep, round 2)
     P.direct_store = direct ? 1 : 0;
     long long stages = ((long long)kSmemMax - kTmaHeaderBytes - (long long)res_bytes - (long long)pad) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -328,19 +329,23 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
   // needs whole rows / planes to stay 16-byte addressable
   const bool trim = P.sched && P.records && P.parts > 1 && (P.HWk % 4) == 0 && getenv("LSFA_NO_ROW_TRIM") == nullptr;
   P.rowrange = trim ? P.sched + (size_t)P.N * P.parts : nullptr;
+  // small batches (the reference's batch-1 operating mode, BASELINE configs[0]): ONE cooperative launch - the kernel's own
+  // consumers build the records before a grid-wide barrier; static work split, whole key planes: no pre-pass, no memset
+  P.coop = (P.records != nullptr && (long long)P.N * P.parts <= kCoopMaxVirtualFrames && getenv("LSFA_TMA_NO_COOP") == nullptr) ? 1 : 0;
+  if (P.coop) {
+    P.sched = nullptr;
+    P.rowrange = nullptr;
+    P.pool_base = P.items;
+  }
   if (P.sched) {  // the per-frame claim counters (and row ranges) start every launch at zero (enqueue-only, no sync)
     cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * P.parts * sizeof(unsigned) * (trim ? 3 : 1), st);
     if (e != cudaSuccess) return e;
   }
-  if (P.records) {  // pre-pass writes the records, the streaming kernel follows in stream order
+  if (P.records && !P.coop) {  // pre-pass writes the records, the streaming kernel follows in stream order
     AggParams R = P;
     R.records = nullptr;
     cudaError_t e = launch_agg_records(R, const_cast<uint4*>(P.records), st);
     if (e != cudaSuccess) return e;
-    // Programmatic dependent launch would let the TMA pipeline fill while the pre-pass runs (~1%),
-    // but with cross-stream event waits between calls (lsfa_b200.host.HostAggregator) we measured
-    // corrupted results on driver 580 / CUDA 12.9, so it is opt-in for experiments only.
-    P.pdl = getenv("LSFA_ENABLE_PDL") ? 1 : 0;
   }
   switch (variant_of(P)) {
     case kVarWarpOnly: return launch_tma_variant<kVarWarpOnly>(P, smem, (int)grid, st);
@@ -408,7 +413,7 @@ cudaError_t launch_agg_nchw_tma2(const AggParams& Pin, size_t smem, cudaStream_t
     cudaError_t e = launch_agg_records(R, const_cast<uint4*>(P.records), st);
     if (e != cudaSuccess) return e;
   }
-  P.pdl = 0;
+  P.coop = 0;
   const int grid = (int)clusters * 2;
   switch (variant_of(P)) {
     case kVarWarpOnly: return launch_tma2_variant<kVarWarpOnly>(P, smem, grid, st);

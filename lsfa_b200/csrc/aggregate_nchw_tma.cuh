@@ -18,6 +18,8 @@
 // caller-supplied scratch) so that SMs that finish early take the tail; each stage carries its
 // (frame, chunk) descriptor in smem.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "aggregate_nchw_plane.cuh"
 
 namespace lsfa {
@@ -39,6 +41,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr int kTmaHeaderBytes = 256;   // 16 mbarriers + one item descriptor per stage
 constexpr int kTmaClaim = 4;           // items per dynamic claim (4 x ~1.8 us of work)
 constexpr int kTmaPoolPercent = 10;    // share of the items left to the dynamic pool (see the producer)
+constexpr int kCoopMaxVirtualFrames = 8;   // up to this many (frame, pixel part) pairs: the one-launch cooperative form
 
 // The 15 consumer warps of both all-TMA kernels (single CTA and 2-CTA cluster): shared-memory-only
 // work on the stages the producer warp fills.  fixed_part < 0: the stage descriptor carries a virtual
@@ -57,7 +60,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
   unsigned o_top[PPT], o_bot[PPT];
   unsigned valid = 0;
   int cur_vf = -1, n = 0;
-  bool byp = false, pdl_synced = false;
+  bool byp = false;
   int s = 0;
   unsigned ph = 0;
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
@@ -99,11 +102,8 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
       byp = has_bypass && (__ldg(P.bypass + n) != 0);
       valid = 0;
       if (P.records != nullptr) {
-        // records come from the pre-pass (agg_records_kernel): two 16-byte loads per pixel slot
-        if (P.pdl && !pdl_synced) {
-          pdl_wait();                 // first use of the pre-pass's output
-          pdl_synced = true;
-        }
+        // records come from the pre-pass (agg_records_kernel) or, cooperative form, from this launch's own consumers
+        // before the grid barrier: two 16-byte loads per pixel slot, from L2 (never the non-coherent path)
         uint4 ra[PPT], rb[PPT];
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
@@ -113,8 +113,8 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
             valid |= 1u << j;
             if (!byp) {
               const uint4* rp = P.records + 2 * ((size_t)n * P.HW + p);
-              ra[j] = __ldg(rp);
-              rb[j] = __ldg(rp + 1);
+              ra[j] = __ldcg(rp);
+              rb[j] = __ldcg(rp + 1);
             }
           }
         }
@@ -302,7 +302,11 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
 
   if (warp == kTmaConsumerWarps) {
     // =========================== producer warp (one elected lane) ===========================
-    if ((tid & 31) == 0) {
+    if ((tid & 31) != 0) {
+      if (P.coop) cooperative_groups::this_grid().sync();     // every thread of the grid takes part in the barrier
+      return;
+    }
+    {
       // ---- work source: a static contiguous share per CTA, then a shared pool claimed dynamically ----
       // Linear item index = virtual frame * chunks + chunk; a "virtual frame" is (frame, pixel part): planes
       // larger than PPT*480 pixels are cut into parts, each with its own sampling records and slice of the
@@ -336,7 +340,6 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       };
       int range_vf = -1;
       uint32_t range_b0 = 0u, range_b1 = 0u;
-      bool range_synced = false;
       auto issue_loads = [&](int s, int vf, int chunk) {
         const int n = vf / P.parts, part = vf - n * P.parts;
         const bool byp = has_bypass && __ldg(P.bypass + n) != 0;
@@ -352,10 +355,6 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
         const bool trimmed = P.rowrange != nullptr;
         if (trimmed && !byp) {
           if (vf != range_vf) {
-            if (P.pdl && !range_synced) {
-              pdl_wait();
-              range_synced = true;
-            }
             range_vf = vf;
             const unsigned hi = __ldcg(P.rowrange + 2 * vf), lo_inv = __ldcg(P.rowrange + 2 * vf + 1);
             range_b0 = hi ? (((uint32_t)(P.Hk - (int)lo_inv) * (uint32_t)P.Wk * 4u) & ~15u) : 0u;
@@ -430,6 +429,8 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
           break;
         }
       }
+      // cooperative form: the first stages are already in flight while the consumers of the whole grid build the records
+      if (P.coop) cooperative_groups::this_grid().sync();
       int s = 0;
       unsigned ph = 0;
       const bool direct = !has_cur && P.direct_store != 0;   // the consumers wrote the output themselves
@@ -457,6 +458,26 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
     return;
   }
 
+  if (P.coop) {
+    // one-launch form (small batches: the reference's batch-1 mode): the index math of the whole batch - at most a pixel
+    // or two per consumer thread of the grid - is done here instead of in a pre-pass kernel, then a grid-wide barrier
+    uint4* rec = const_cast<uint4*>(P.records);
+    const long long total = (long long)P.N * P.HW;
+    for (long long i = (long long)blockIdx.x * kTmaConsumers + tid; i < total; i += (long long)gridDim.x * kTmaConsumers) {
+      const int n = (int)(i / P.HW);
+      const int p = (int)(i - (long long)n * P.HW);
+      if (has_bypass && __ldg(P.bypass + n) != 0) continue;
+      const int y = p / P.W, x = p - y * P.W;
+      const PixelLoads ld = issue_pixel_loads(P, n, y, x);
+      const PixelRec t = finish_pixel(P, ld, n, y, x);
+      uint4 a, b;
+      pack_record(t, a, b);
+      __stcg(rec + 2 * i, a);
+      __stcg(rec + 2 * i + 1, b);
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+  }
   tma_consumer_loop<K, PPT, VAR>(P, full, done, desc, ring, res_s, rnet_s, tid, -1);
 }
 
@@ -465,21 +486,29 @@ cudaError_t launch_tma_variant(const AggParams& P, size_t smem, int grid, cudaSt
 
 #define LSFA_TMA_FOREACH_KP(X) X(1, 1) X(1, 3) X(1, 5) X(1, 9) X(2, 1) X(2, 3) X(2, 5) X(2, 9)
 
+// the opt-in to 227 KB of dynamic shared memory is a per-function, per-device attribute: set it the first time a device
+// sees the instantiation, not on every launch (idempotent: a race between two host threads sets it twice)
 #define LSFA_TMA_LAUNCH(VAR, KK, PP)                                                              \
   if (P.K == KK && ppt == PP) {                                                                   \
     auto kfn = agg_nchw_tma_kernel<KK, PP, VAR>;                                                  \
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                               \
+    static bool attr_done[64];                                                                    \
+    int dev_ = 0;                                                                                 \
+    cudaGetDevice(&dev_);                                                                         \
+    if (dev_ < 0 || dev_ >= 64 || !attr_done[dev_]) {                                             \
+      cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); \
+      if (e != cudaSuccess) return e;                                                             \
+      if (dev_ >= 0 && dev_ < 64) attr_done[dev_] = true;                                         \
+    }                                                                                             \
     cudaLaunchConfig_t cfg = {};                                                                  \
     cfg.gridDim = dim3((unsigned)grid);                                                           \
     cfg.blockDim = dim3(kTmaThreads);                                                             \
     cfg.dynamicSmemBytes = smem;                                                                  \
     cfg.stream = st;                                                                              \
     cudaLaunchAttribute attr[1];                                                                  \
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
-    attr[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+    attr[0].id = cudaLaunchAttributeCooperative;                                                  \
+    attr[0].val.cooperative = 1;                                                                  \
     cfg.attrs = attr;                                                                             \
-    cfg.numAttrs = P.pdl ? 1 : 0;                                                                 \
+    cfg.numAttrs = P.coop ? 1 : 0;                                                                \
     return cudaLaunchKernelEx(&cfg, kfn, P);                                                      \
   }
 

@@ -434,8 +434,12 @@ int lsfa_warp_scale_aggregate_num_launches(const LsfaAggArgs* args) {
     if (cosine_partials_ws_bytes(args) && args->workspace && args->workspace_bytes >= full && args->force_generic != 1) ++n;
   }
   const size_t need = lsfa_warp_scale_aggregate_workspace_bytes(args);
-  if (args->workspace && args->workspace_bytes >= need && args->force_generic != 1 && args->force_generic != 2)
-    ++n;                                                             // record pre-pass (all-TMA kernel)
+  if (args->workspace && args->workspace_bytes >= need && args->force_generic != 1 && args->force_generic != 2) {
+    // record pre-pass of the all-TMA kernel - except for small batches (N x pixel parts <= 8), which the kernel serves in
+    // ONE cooperative launch: its own consumers build the records before a grid-wide barrier
+    const long long parts = ((long long)args->H * args->W + 4319) / 4320;
+    if (args->force_generic == 4 || (long long)args->N * parts > 8) ++n;
+  }
   return n;
 }
 

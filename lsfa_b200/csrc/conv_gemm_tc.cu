@@ -127,16 +127,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
          | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// A work item is a PAIR of pixel tiles (image b and image b + NB/2, one weight tile for both).  The pair items that would
+// form a last, partly filled wave of the persistent grid are cut into two SINGLE-tile items each (half the time): with
+// T pair items on G CTAs the step costs floor(T/G) + 0.5 waves instead of ceil(T/G) when 2*(T mod G) <= G.
 struct Item {
-  int chunk, img0, img1, x0, y0;
+  int chunk, pair, img0, img1, x0, y0;
+  int single;     // 1: only accumulator 0 is used, on image img0
+  int which;      // single: 0 = the pair's first image, 1 = its second
 };
 __device__ __forceinline__ Item decode_item(const ConvParams& P, int item) {
   Item it;
+  it.single = item >= P.pair_items;
+  it.which = 0;
+  if (it.single) {
+    const int j = item - P.pair_items;
+    it.which = j & 1;
+    item = P.pair_items + (j >> 1);
+  }
   it.chunk = item % P.n_chunks;
   int t = item / P.n_chunks;
   const int tile = t % (P.tiles_x * P.tiles_y);
-  it.img0 = t / (P.tiles_x * P.tiles_y);
-  it.img1 = it.img0 + P.NB / 2;
+  it.pair = t / (P.tiles_x * P.tiles_y);
+  it.img0 = it.pair + (it.which ? P.NB / 2 : 0);
+  it.img1 = it.pair + P.NB / 2;
   it.x0 = (tile % P.tiles_x) * P.BW;
   it.y0 = (tile / P.tiles_x) * P.BH;
   return it;
@@ -202,9 +215,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int dy = P.taps == 9 ? tap / 3 - 1 : 0, dx = P.taps == 9 ? tap % 3 - 1 : 0;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          mbar_expect_tx(&full[stage], it.single ? A_BYTES + B_BYTES : STAGE_BYTES);
           tma_load_4d(st, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, it.img0, &full[stage]);
-          tma_load_4d(st + A_BYTES, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, it.img1, &full[stage]);
+          if (!it.single) tma_load_4d(st + A_BYTES, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, it.img1, &full[stage]);
           tma_load_2d(st + 2 * A_BYTES, &tmB, tap * P.Cin + kc * BK, it.chunk * BN, &full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -216,6 +229,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, tphase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const bool single = item >= P.pair_items;
         mbar_wait(tmem_empty, tphase ^ 1);        // the epilogue has drained both accumulators
         tcgen05_fence_after();
         for (int ks = 0; ks < P.k_steps; ++ks) {
@@ -229,7 +243,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) start-address field
             umma_bf16(tmem_base, da0 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
-            umma_bf16(tmem_base + BN, da1 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+            if (!single) umma_bf16(tmem_base + BN, da1 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
           }
           umma_commit(&empty[stage]);             // frees the stage once these MMAs have read it
           if (ks == P.k_steps - 1) umma_commit(tmem_full);
@@ -255,8 +269,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tmem_full, tphase);
       tcgen05_fence_after();
       if (EPI == EPI_STORE_RELU || EPI == EPI_STORE) {
+        const int n_acc = it.single ? 1 : 2;
 #pragma unroll 1
-        for (int acc = 0; acc < 2; ++acc) {
+        for (int acc = 0; acc < n_acc; ++acc) {
           const int img = acc ? it.img1 : it.img0;
           __nv_bfloat16* dst = P.out + (((size_t)img * P.H * P.W + pix) * P.Cout + (size_t)it.chunk * BN);
 #pragma unroll 1
@@ -305,8 +320,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           dst[2 * NP] = swc;
         }
       } else {   // EPI_NQ
+        const int n_acc = it.single ? 1 : 2;
 #pragma unroll 1
-        for (int acc = 0; acc < 2; ++acc) {
+        for (int acc = 0; acc < n_acc; ++acc) {
           float q[NQ_MID];
 #pragma unroll
           for (int j = 0; j < NQ_MID; ++j) q[j] = s_nq[j];                 // Nq_conv2 bias
@@ -333,7 +349,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < NQ_MID; ++j) o = fmaf(s_nq[NQ_MID + j], fmaxf(q[j], 0.f), o);   // ReLU (SYM:100), Nq_conv3
           // image b of Concat_0(warp, conv) is the warped feature -> logits[:,0]; image b + N the current one -> [:,1]
-          if (valid) P.logits[((size_t)it.img0 * 2 + acc) * P.H * P.W + pix] = o;
+          if (valid) P.logits[((size_t)it.pair * 2 + (it.single ? it.which : acc)) * P.H * P.W + pix] = o;
         }
       }
       tcgen05_fence_before();
@@ -453,7 +469,18 @@ const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int
   P.n_chunks = P.Cout / BN;
   P.kc_per_tap = P.Cin / BK;
   P.k_steps = P.taps * P.kc_per_tap;
-  P.num_items = (P.NB / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
+  P.pair_items = (P.NB / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
+  P.num_items = P.pair_items;
+  if (epi != EPI_COSINE && 2 * P.pair_items <= sms) {   // fewer items than half the SMs: every tile on its own CTA
+    P.num_items = 2 * P.pair_items;
+    P.pair_items = 0;
+  } else if (epi != EPI_COSINE && P.pair_items > sms) { // cut the pair items of a partly filled last wave in two
+    const int rem = P.pair_items % sms;
+    if (rem > 0 && 2 * rem <= sms) {
+      P.pair_items -= rem;
+      P.num_items = P.pair_items + 2 * rem;
+    }
+  }
   CUtensorMap tmA, tmB;
   if (const char* e = make_maps(x, w, P, &tmA, &tmB)) return e;
   switch (epi) {

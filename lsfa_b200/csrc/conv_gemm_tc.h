@@ -18,7 +18,7 @@ struct ConvParams {
   float* logits;                        // NQ: (NB/2, 2, H, W) f32
   const float *nq_w2, *nq_b2, *nq_w3, *nq_b3;   // NQ tail: (16,256), (16), (16), (1)
   // tiling (filled by launch_conv)
-  int BW, BH, tiles_x, tiles_y, n_chunks, kc_per_tap, k_steps, num_items;
+  int BW, BH, tiles_x, tiles_y, n_chunks, kc_per_tap, k_steps, num_items, pair_items;
 };
 
 // nullptr = enqueued; otherwise a static message (nothing was launched)

@@ -61,7 +61,8 @@ struct AggParams {
   unsigned* sched;             // zeroed counter(s) for dynamic work claims, or NULL = static split
   long long pool_base;         // all-TMA kernel: items [0,pool_base) are split statically, the rest claimed from sched[0]
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
-  int pdl;                     // launched as a programmatic dependent of the record pre-pass
+  int coop;                    // all-TMA NCHW kernel launched cooperatively: its own consumers build the records, then a
+                               // grid-wide barrier - the one-launch form for small batches (no pre-pass, no memset)
   int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory
   int direct_store;            // all-TMA NCHW kernel, variants without cur: consumers store to global themselves
   unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:
@@ -449,10 +450,6 @@ __device__ __forceinline__ void pack_record(const PixelRec& t, uint4& a, uint4& 
                  (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16));
 }
 
-// programmatic dependent launch (PDL): the pre-pass lets its dependent start early; the dependent
-// waits for the pre-pass's memory only where it first needs it
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (global -> shared), SASS: SYNCS / UBLKCP

@@ -362,6 +362,33 @@ LSFA_API int lsfa_nq_logits_bf16_nhwc(const void* x, const void* w1, const float
                                       const float* w3, const float* b3, float* logits, int N, int H, int W, int C,
                                       void* stream);
 
+/* ---- backward of the fused operator's tails (get_train_symbol SYM:306-338) -------------
+ * Gradients of  out = wc*cur + ww*( BilinearSampler(key, GridGenerator(flow)) * scale_map + rnet_conv0(res) ),
+ * (ww,wc) by weight_mode (NONE | ADD | MEAN | LOGITS = 2-way softmax), bypass frames: out = cur, with respect to every
+ * differentiable input, from d/d(out).  `fwd` is the forward's argument block (layout NCHW float32; `out` is not read
+ * and may be any non-NULL pointer); each gradient has an OpReqType (NULL pointer or LSFA_REQ_NULL skips it).
+ *   grad_key   (N,C,H,W)   needs private keys (key_index NULL) and key planes of the output's size
+ *   grad_flow  (N,2,H,W)   LSFA_FLOW_PREPOOLED (flow in feature cells) or LSFA_FLOW_GRID (then it is d/d(grid));
+ *                          raw motion vectors are integer data and get no gradient (SYM:319-321: the MV is data)
+ *   grad_scale, grad_cur (N,C,H,W); grad_logits (N,2,H,W); grad_res (N,3,H,W); grad_rnet_w (C,3), grad_rnet_b (C)
+ * One pass over the feature streams (agg_tail_backward_kernel) + the a7/a8 gather backward for key/flow; every
+ * reduction is summed in a fixed order (deterministic).  LSFA_W_COSINE has no backward here (its embeddings are inputs
+ * of this library, produced by convolutions outside it).  workspace: the _workspace_bytes query, 256-byte aligned. */
+typedef struct LsfaAggGrads {
+  int32_t struct_bytes;        /* = sizeof(LsfaAggGrads) */
+  const float* out_grad;       /* (N,C,H,W) */
+  float* grad_key;    int32_t req_key;
+  float* grad_flow;   int32_t req_flow;
+  float* grad_scale;  int32_t req_scale;
+  float* grad_cur;    int32_t req_cur;
+  float* grad_logits; int32_t req_logits;
+  float* grad_res;    int32_t req_res;
+  float* grad_rnet_w; float* grad_rnet_b; int32_t req_rnet;
+  void*  workspace;   size_t workspace_bytes;
+} LsfaAggGrads;
+LSFA_API size_t lsfa_warp_scale_aggregate_backward_workspace_bytes(const LsfaAggArgs* fwd, const LsfaAggGrads* grads);
+LSFA_API int    lsfa_warp_scale_aggregate_backward_f32_nchw(const LsfaAggArgs* fwd, const LsfaAggGrads* grads, void* stream);
+
 /* layout helpers for the harness: NCHW f32 <-> NHWC {f32,bf16} */
 LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int dst_layout,
                       void* stream);

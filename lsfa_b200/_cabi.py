@@ -58,6 +58,20 @@ class LsfaAggArgs(C.Structure):
     ]
 
 
+class LsfaAggGrads(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("out_grad", C.c_void_p),
+        ("grad_key", C.c_void_p), ("req_key", C.c_int32),
+        ("grad_flow", C.c_void_p), ("req_flow", C.c_int32),
+        ("grad_scale", C.c_void_p), ("req_scale", C.c_int32),
+        ("grad_cur", C.c_void_p), ("req_cur", C.c_int32),
+        ("grad_logits", C.c_void_p), ("req_logits", C.c_int32),
+        ("grad_res", C.c_void_p), ("req_res", C.c_int32),
+        ("grad_rnet_w", C.c_void_p), ("grad_rnet_b", C.c_void_p), ("req_rnet", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 class LsfaHostAggArgs(C.Structure):
     _fields_ = [
         ("struct_bytes", C.c_int32),
@@ -118,6 +132,8 @@ PROTOTYPES = {
     "lsfa_embed_cosine_logits_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
     "lsfa_embed_cosine_logits_bf16_nhwc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _P]),
     "lsfa_nq_logits_bf16_nhwc": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "lsfa_warp_scale_aggregate_backward_workspace_bytes": (_SZ, [C.POINTER(LsfaAggArgs), C.POINTER(LsfaAggGrads)]),
+    "lsfa_warp_scale_aggregate_backward_f32_nchw": (_I, [C.POINTER(LsfaAggArgs), C.POINTER(LsfaAggGrads), _P]),
     "lsfa_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lsfa_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }

@@ -8,6 +8,7 @@
 
 #include "lsfa_device.cuh"
 #include "conv_gemm_tc.h"
+#include "aggregate_backward.h"
 
 namespace lsfa {
 // aggregate_nchw.cu
@@ -697,6 +698,102 @@ int lsfa_nq_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, con
   P.NB = 2 * N; P.H = H; P.W = W; P.Cin = C; P.Cout = 256; P.taps = 9;
   P.bias = b1; P.logits = logits; P.nq_w2 = w2; P.nq_b2 = b2; P.nq_w3 = w3; P.nq_b3 = b3;
   return tc_result(lsfa::tc::launch_conv(x, w1, P, lsfa::tc::EPI_NQ, tc_sm_count(), as_stream(stream)), "nq_logits");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward of the fused operator's tails (aggregate_backward.cu) + a7/a8 backward (sampler_backward.cu)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct BwdPlan {
+  bool want_key, want_flow, want_scale, want_cur, want_logits, want_res, want_rnet, want_gw, pool_flow;
+  size_t tail_ws, flow_ws, samp_ws;
+};
+inline bool wanted(const void* p, int req) { return p != nullptr && req != LSFA_REQ_NULL; }
+int plan_backward(const LsfaAggArgs* a, const LsfaAggGrads* g, BwdPlan& B) {
+  if (!a || !g) return fail(LSFA_E_BADARG, "fwd and grads are required");
+  if (g->struct_bytes != (int32_t)sizeof(LsfaAggGrads)) return fail(LSFA_E_BADARG, "grads->struct_bytes=%d, expected %zu", g->struct_bytes, sizeof(LsfaAggGrads));
+  if (a->struct_bytes != (int32_t)sizeof(LsfaAggArgs)) return fail(LSFA_E_BADARG, "fwd->struct_bytes=%d, expected %zu", a->struct_bytes, sizeof(LsfaAggArgs));
+  if (a->layout != LSFA_LAYOUT_NCHW_F32) return fail(LSFA_E_UNSUPPORTED, "the backward is built for the NCHW float32 layout");
+  if (a->weight_mode == LSFA_W_COSINE) return fail(LSFA_E_UNSUPPORTED, "LSFA_W_COSINE has no backward (its embeddings are inputs produced outside this library)");
+  const int reqs[7] = {g->req_key, g->req_flow, g->req_scale, g->req_cur, g->req_logits, g->req_res, g->req_rnet};
+  for (int r : reqs) if (!valid_req(r)) return fail(LSFA_E_BADARG, "unknown req %d", r);
+  B.want_key = wanted(g->grad_key, g->req_key);
+  B.want_flow = wanted(g->grad_flow, g->req_flow);
+  B.want_scale = wanted(g->grad_scale, g->req_scale);
+  B.want_cur = wanted(g->grad_cur, g->req_cur);
+  B.want_logits = wanted(g->grad_logits, g->req_logits);
+  B.want_res = wanted(g->grad_res, g->req_res);
+  B.want_rnet = wanted(g->grad_rnet_w, g->req_rnet);
+  if (B.want_rnet && !g->grad_rnet_b) return fail(LSFA_E_BADARG, "grad_rnet_w and grad_rnet_b go together");
+  if (B.want_scale && !a->scale_map) return fail(LSFA_E_BADARG, "grad_scale requested but the forward had no scale_map");
+  if (B.want_cur && a->weight_mode == LSFA_W_NONE) return fail(LSFA_E_BADARG, "grad_cur requested but weight_mode is NONE");
+  if (B.want_logits && a->weight_mode != LSFA_W_LOGITS) return fail(LSFA_E_BADARG, "grad_logits requested but weight_mode is not LOGITS");
+  if ((B.want_res || B.want_rnet) && !a->res) return fail(LSFA_E_BADARG, "residual gradients requested but the forward had no res");
+  if (B.want_flow && a->flow_kind != LSFA_FLOW_PREPOOLED && a->flow_kind != LSFA_FLOW_GRID)
+    return fail(LSFA_E_BADARG, "grad_flow needs LSFA_FLOW_PREPOOLED or LSFA_FLOW_GRID: raw motion vectors are integer data (SYM:319-321)");
+  if (B.want_key || B.want_flow) {
+    if (a->key_index) return fail(LSFA_E_UNSUPPORTED, "grad_key / grad_flow need private keys (key_index NULL)");
+    if (a->flow_kind == LSFA_FLOW_COVIAR_I32) return fail(LSFA_E_UNSUPPORTED, "grad_key with LSFA_FLOW_COVIAR_I32: prepare and pool the MV first");
+    const int Hk = a->key_h > 0 ? a->key_h : a->H, Wk = a->key_w > 0 ? a->key_w : a->W;
+    if (a->flow_kind != LSFA_FLOW_GRID && (Hk != a->H || Wk != a->W)) return fail(LSFA_E_UNSUPPORTED, "grad_key with a flow needs key planes of the output's size");
+  }
+  if (a->N <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0) return fail(LSFA_E_SHAPE, "non-positive dims");
+  B.want_gw = B.want_key || B.want_flow;
+  B.pool_flow = B.want_gw && (a->flow_kind == LSFA_FLOW_RAW_I32 || a->flow_kind == LSFA_FLOW_RAW_F32);
+  const int HW = a->H * a->W;
+  B.tail_ws = lsfa::tail_backward_workspace_bytes(a->N, a->C, HW, B.want_gw, B.want_logits, B.want_res || B.want_rnet);
+  B.flow_ws = B.pool_flow ? (((size_t)a->N * 2 * HW * 4 + 255) & ~(size_t)255) : 0;
+  const int Hk = a->key_h > 0 ? a->key_h : a->H, Wk = a->key_w > 0 ? a->key_w : a->W;
+  B.samp_ws = B.want_gw ? ((lsfa::bwd_workspace_bytes(a->N, Hk * Wk, HW) + 255) & ~(size_t)255) : 0;
+  return LSFA_OK;
+}
+}  // namespace
+
+size_t lsfa_warp_scale_aggregate_backward_workspace_bytes(const LsfaAggArgs* fwd, const LsfaAggGrads* grads) {
+  BwdPlan B;
+  if (plan_backward(fwd, grads, B) != LSFA_OK) return 0;
+  return B.tail_ws + B.flow_ws + B.samp_ws;
+}
+
+int lsfa_warp_scale_aggregate_backward_f32_nchw(const LsfaAggArgs* fwd, const LsfaAggGrads* g, void* stream) {
+  BwdPlan B;
+  if (int r = plan_backward(fwd, g, B)) return r;
+  if (!g->out_grad) return fail(LSFA_E_BADARG, "out_grad is required");
+  lsfa::AggParams P;
+  if (int r = build_params(fwd, P)) return r;
+  if (P.HWk > 16383) return fail(LSFA_E_UNSUPPORTED, "key planes above 16,383 pixels are not supported by the backward");
+  const size_t need = B.tail_ws + B.flow_ws + B.samp_ws;
+  if (!g->workspace || g->workspace_bytes < need) return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", need);
+  if (reinterpret_cast<uintptr_t>(g->workspace) & 255) return fail(LSFA_E_ALIGN, "workspace must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  char* ws = static_cast<char*>(g->workspace);
+  float* gw = nullptr;
+  lsfa::TailBwdRequest R{};
+  R.out_grad = g->out_grad;
+  R.grad_scale = B.want_scale ? g->grad_scale : nullptr; R.add_scale = g->req_scale == LSFA_REQ_ADD;
+  R.grad_cur = B.want_cur ? g->grad_cur : nullptr;       R.add_cur = g->req_cur == LSFA_REQ_ADD;
+  R.grad_logits = B.want_logits ? g->grad_logits : nullptr; R.add_logits = g->req_logits == LSFA_REQ_ADD;
+  R.grad_res = B.want_res ? g->grad_res : nullptr;       R.add_res = g->req_res == LSFA_REQ_ADD;
+  R.grad_rnet_w = B.want_rnet ? g->grad_rnet_w : nullptr; R.grad_rnet_b = B.want_rnet ? g->grad_rnet_b : nullptr;
+  R.add_rnet = g->req_rnet == LSFA_REQ_ADD;
+  R.want_gw = B.want_gw;
+  R.gw_out = &gw;
+  if (int r = cuda_result(lsfa::launch_tail_backward(P, R, ws, st), "tail backward launch")) return r;
+  if (!B.want_gw) return LSFA_OK;
+  ws += B.tail_ws;
+  const float* coords = static_cast<const float*>(fwd->flow);
+  int is_flow = fwd->flow_kind != LSFA_FLOW_GRID;
+  if (B.pool_flow) {                         // a3+a5+a6 once more: the sampler's backward wants the pooled flow
+    float* pooled = reinterpret_cast<float*>(ws);
+    ws += B.flow_ws;
+    if (int r = cuda_result(lsfa::launch_mv_pool(fwd->flow, fwd->flow_kind == LSFA_FLOW_RAW_I32, pooled, fwd->N, fwd->mv_h, fwd->mv_w, fwd->H,
+                                                 fwd->W, fwd->im_scale / 16.0, fwd->pool_mode, st), "mv_pool launch")) return r;
+    coords = pooled;
+  }
+  const int Hk = fwd->key_h > 0 ? fwd->key_h : fwd->H, Wk = fwd->key_w > 0 ? fwd->key_w : fwd->W;
+  return sampler_backward_common(static_cast<const float*>(fwd->key), coords, is_flow, gw, B.want_key ? g->grad_key : nullptr,
+                                 B.want_flow ? g->grad_flow : nullptr, fwd->N, fwd->C, Hk, Wk, fwd->H, fwd->W,
+                                 B.want_key ? g->req_key : LSFA_REQ_NULL, B.want_flow ? g->req_flow : LSFA_REQ_NULL, ws, B.samp_ws, 0, stream);
 }
 
 }  // extern "C"

@@ -471,6 +471,54 @@ class PreparedAggregate:
         return self.out
 
 
+def warp_scale_aggregate_backward(out_grad, key, flow, *, want=("key", "flow", "scale", "cur", "logits", "res", "rnet"), **kw):
+    """Backward of ``warp_scale_aggregate`` (NCHW float32; modes none/add/mean/logits; SYM:306-338 needs it for training):
+    returns a dict of the gradients that exist for these inputs among ``want`` - 'key', 'flow' (prepooled flow or grid
+    only: raw motion vectors are data), 'scale', 'cur', 'logits', 'res', 'rnet_w' + 'rnet_b'.  ``kw`` = the forward's
+    keyword arguments."""
+    import ctypes
+    kw = dict(kw)
+    kw.pop("out", None)
+    kw.pop("req", None)
+    kw["workspace"] = False
+    _dev(out_grad, "out_grad", torch.float32)
+    args, _out, keep = _build_args(key, flow, **kw)
+    if tuple(out_grad.shape) != tuple(_out.shape):
+        raise ValueError("out_grad has shape %s, expected %s" % (tuple(out_grad.shape), tuple(_out.shape)))
+    g = A.LsfaAggGrads()
+    g.struct_bytes = ctypes.sizeof(A.LsfaAggGrads)
+    g.out_grad = out_grad.data_ptr()
+    res = {}
+    fk = kw.get("flow_kind", "flow")
+    mode = kw.get("weight_mode", "none")
+
+    def mk(name, like, cond):
+        if name in want and cond:
+            res[name] = torch.empty_like(like)
+            return res[name].data_ptr(), A.REQ_WRITE
+        return None, A.REQ_NULL
+    g.grad_key, g.req_key = mk("key", key, kw.get("key_index") is None)
+    g.grad_flow, g.req_flow = mk("flow", flow, fk in ("flow", "grid"))
+    g.grad_scale, g.req_scale = mk("scale", kw.get("scale_map"), kw.get("scale_map") is not None)
+    g.grad_cur, g.req_cur = mk("cur", kw.get("cur"), kw.get("cur") is not None and mode != "none")
+    g.grad_logits, g.req_logits = mk("logits", kw.get("logits"), mode == "logits")
+    g.grad_res, g.req_res = mk("res", kw.get("res"), kw.get("res") is not None)
+    if "rnet" in want and kw.get("res") is not None:
+        res["rnet_w"] = torch.empty_like(kw["rnet_w"])
+        res["rnet_b"] = torch.empty_like(kw["rnet_b"])
+        g.grad_rnet_w, g.grad_rnet_b, g.req_rnet = res["rnet_w"].data_ptr(), res["rnet_b"].data_ptr(), A.REQ_WRITE
+    lib = A.load()
+    need = lib.lsfa_warp_scale_aggregate_backward_workspace_bytes(args, g)
+    if need == 0:
+        A.check(lib.lsfa_warp_scale_aggregate_backward_f32_nchw(args, g, _stream()))     # raises with the library's message
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=key.device)
+    off = (-ws.data_ptr()) % 256
+    g.workspace, g.workspace_bytes = ws.data_ptr() + off, need
+    A.check(lib.lsfa_warp_scale_aggregate_backward_f32_nchw(args, g, _stream()))
+    del keep
+    return res
+
+
 def num_launches(**kw) -> int:
     args, _, _ = _build_args(**kw)
     return A.load().lsfa_warp_scale_aggregate_num_launches(args)

@@ -118,3 +118,53 @@ def _(key, flow, cur, scale_map, logits, bypass, weight_mode, flow_kind, im_scal
     if layout == 0:
         return key.new_empty((n, key.shape[1], h, w))
     return key.new_empty((n, h, w, key.shape[3]))
+
+
+# backward of the fused operator (csrc/aggregate_backward.cu): NCHW float32, modes none/add/mean/logits; raw motion vectors
+# are data (no gradient), a prepooled flow / grid gets one
+@torch.library.custom_op("lsfa::warp_scale_aggregate_backward", mutates_args=())
+def warp_scale_aggregate_backward(out_grad: torch.Tensor, key: torch.Tensor, flow: torch.Tensor, cur: Optional[torch.Tensor],
+                                  scale_map: Optional[torch.Tensor], logits: Optional[torch.Tensor],
+                                  bypass: Optional[torch.Tensor], weight_mode: int, flow_kind: int,
+                                  im_scale: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    g = ops.warp_scale_aggregate_backward(out_grad.contiguous(), key, flow, cur=cur, scale_map=scale_map, logits=logits, bypass=bypass,
+                                          weight_mode=_MODES[weight_mode], flow_kind=_FLOWS[flow_kind], im_scale=im_scale)
+    z = lambda t: torch.zeros_like(t) if t is not None else out_grad.new_zeros(1)  # noqa: E731
+    flow_like = flow if flow.dtype == torch.float32 else None
+    return (g["key"], g.get("flow", z(flow_like)), g.get("cur", z(cur)), g.get("scale", z(scale_map)), g.get("logits", z(logits)))
+
+
+@warp_scale_aggregate_backward.register_fake
+def _(out_grad, key, flow, cur, scale_map, logits, bypass, weight_mode, flow_kind, im_scale):
+    e = lambda t: torch.empty_like(t) if t is not None else out_grad.new_empty(1)  # noqa: E731
+    return torch.empty_like(key), e(flow if flow.dtype == torch.float32 else None), e(cur), e(scale_map), e(logits)
+
+
+def _wsa_setup(ctx, inputs, output):
+    key, flow, cur, scale_map, logits, bypass, weight_mode, flow_kind, im_scale, layout = inputs
+    if layout != 0 or weight_mode == 4:
+        ctx.unsupported = "the backward is built for NCHW float32 and the modes none/add/mean/logits"
+        return
+    ctx.unsupported = None
+    ctx.meta = (weight_mode, flow_kind, im_scale)
+    ctx.has = (cur is not None, scale_map is not None, logits is not None, bypass is not None)
+    ctx.save_for_backward(*[t for t in (key, flow, cur, scale_map, logits, bypass) if t is not None])
+
+
+def _wsa_backward(ctx, grad_out):
+    if ctx.unsupported:
+        raise RuntimeError("lsfa::warp_scale_aggregate: " + ctx.unsupported)
+    saved = list(ctx.saved_tensors)
+    key, flow = saved[0], saved[1]
+    rest = saved[2:]
+    opt = []
+    for present in ctx.has:
+        opt.append(rest.pop(0) if present else None)
+    cur, scale_map, logits, bypass = opt
+    weight_mode, flow_kind, im_scale = ctx.meta
+    gk, gf, gc, gs, gl = warp_scale_aggregate_backward(grad_out, key, flow, cur, scale_map, logits, bypass, weight_mode, flow_kind, im_scale)
+    return (gk, gf if (flow_kind in (0, 1) and flow.dtype == torch.float32) else None, gc if cur is not None else None,
+            gs if scale_map is not None else None, gl if (logits is not None and weight_mode == 3) else None, None, None, None, None, None)
+
+
+warp_scale_aggregate.register_autograd(_wsa_backward, setup_context=_wsa_setup)

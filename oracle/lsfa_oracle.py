@@ -620,6 +620,50 @@ def key_frame_nq_full(feat_key_old, flow, scale_map, conv_feat, nq_params, is_fi
     return choose_feat(np.asarray(conv_feat, F32), out, is_first) if is_first is not None else out
 
 
+def warp_scale_aggregate_backward(out_grad, key, flow, cur=None, scale_map=None, res=None, rnet_w=None, rnet_b=None,
+                                  weight_mode=W_NONE, logits=None, bypass=None):
+    """Gradients of warp_scale_aggregate (modes none/add/mean/logits) w.r.t. key, flow, scale_map, cur, logits, res,
+    rnet_w, rnet_b from d/d(out) - float64 chain rule on top of the a7/a8 backward restatement (get_train_symbol
+    SYM:306-338 differentiates exactly these operators).  Returns a dict (entries only for inputs that exist)."""
+    g = np.asarray(out_grad, F64)
+    N, C, H, W = g.shape
+    wp = np.asarray(warp(key, flow), F64)
+    sc = np.ones_like(wp) if scale_map is None else np.asarray(scale_map, F64)
+    src0 = wp * sc
+    if res is not None:
+        rw = np.asarray(rnet_w, F64).reshape(C, 3)
+        src0 = src0 + np.einsum("cj,njhw->nchw", rw, np.asarray(res, F64)) + np.asarray(rnet_b, F64).reshape(1, C, 1, 1)
+    ww = np.ones((N, 1, H, W))
+    wc = np.zeros((N, 1, H, W))
+    if weight_mode == W_ADD:
+        wc[:] = 1.0
+    elif weight_mode == W_MEAN:
+        ww[:] = 0.5
+        wc[:] = 0.5
+    elif weight_mode == W_LOGITS:
+        a, b = softmax_pair(logits[:, 0:1], logits[:, 1:2])
+        ww, wc = np.asarray(a, F64), np.asarray(b, F64)
+    live = np.ones((N, 1, 1, 1)) if bypass is None else (np.asarray(bypass).reshape(N, 1, 1, 1) == 0).astype(F64)
+    out = {}
+    gs0 = ww * g * live                                   # d/d(src0)
+    if cur is not None and weight_mode != W_NONE:
+        out["cur"] = (wc * g * live + g * (1.0 - live)).astype(F32)
+    if scale_map is not None:
+        out["scale"] = (gs0 * wp).astype(F32)
+    gk, gf = warp_backward(key, flow, (gs0 * sc).astype(F32))
+    out["key"], out["flow"] = gk, gf
+    if weight_mode == W_LOGITS:
+        t1 = np.sum(g * src0, axis=1, keepdims=True)
+        t2 = np.sum(g * np.asarray(cur, F64), axis=1, keepdims=True)
+        d = ww * wc * (t1 - t2) * live
+        out["logits"] = np.concatenate([d, -d], axis=1).astype(F32)
+    if res is not None:
+        out["res"] = np.einsum("cj,nchw->njhw", rw, gs0).astype(F32)
+        out["rnet_w"] = np.einsum("nchw,njhw->cj", gs0, np.asarray(res, F64)).astype(F32)
+        out["rnet_b"] = gs0.sum(axis=(0, 2, 3)).astype(F32)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # Stated-tolerance bf16 variant of the two networks (the tensor-core kernels of SURVEY 8f rank 2):
 # same graphs as embed_net / nq_net above with the product's rounding points made explicit -

@@ -300,6 +300,14 @@ LSFA_API size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width)
 LSFA_API int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height,
                                     int width, int32_t* mv_out, void* workspace, size_t workspace_bytes,
                                     void* stream);
+/* The same with the algorithm pinned (ablation / tests): algo 0 auto, 1 the per-frame field form (owner map + gather, the
+ * accumulated field crosses HBM every P-frame), 2 the cell-index back-trace (a chain of T look-ups per pixel through a
+ * per-8x8-cell index; the field is written once; workspace lsfa_mv_accumulate_trace_workspace_bytes, N*T <= 65535).
+ * lsfa_mv_accumulate_i32 = auto: the back-trace whenever it fits.  lsfa_mv_accumulate_workspace_bytes covers both. */
+LSFA_API size_t lsfa_mv_accumulate_trace_workspace_bytes(int N, int T, int height, int width);
+LSFA_API int lsfa_mv_accumulate_algo_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height,
+                                         int width, int32_t* mv_out, void* workspace, size_t workspace_bytes, int algo,
+                                         void* stream);
 /* residual of coviar_data_loader.c:141-175: res = cur - iframe[(x,y) - mv]; frames (N,height,width,3) uint8
  * BGR, mv the accumulated field above, res (N,height,width,3) int32. */
 LSFA_API int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res,

@@ -121,6 +121,8 @@ PROTOTYPES = {
     "lsfa_choose_feat_f32": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P]),
     "lsfa_mv_accumulate_workspace_bytes": (_SZ, [_I, _I, _I]),
     "lsfa_mv_accumulate_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _P]),
+    "lsfa_mv_accumulate_trace_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "lsfa_mv_accumulate_algo_i32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _SZ, _I, _P]),
     "lsfa_coviar_residual_u8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "lsfa_bilinear_sampler_backward_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I, _I]),
     "lsfa_bilinear_sampler_backward_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _SZ, _I, _P]),

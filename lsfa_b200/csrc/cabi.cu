@@ -56,7 +56,8 @@ cudaError_t launch_blend_logits(const float* src0, const float* cur, const float
                                 float* out, int N, int C, int HW, cudaStream_t st);
 // coviar_accumulate.cu
 cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
-                                 int* mv_out, void* workspace, cudaStream_t st);
+                                 int* mv_out, void* workspace, size_t workspace_bytes, int algo, cudaStream_t st);
+size_t mvacc_trace_workspace_bytes(int N, int T, int height, int width);
 cudaError_t launch_coviar_residual(const unsigned char* iframe, const unsigned char* cur, const int* mv, int* res, int N,
                                    int height, int width, cudaStream_t st);
 // sampler_backward.cu
@@ -511,19 +512,37 @@ size_t lsfa_mv_accumulate_workspace_bytes(int N, int height, int width) {
   return (size_t)N * height * width * (2 * 8 + 4);      // two (x,y) int2 fields + the owner map
 }
 
-int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height, int width,
-                           int32_t* mv_out, void* workspace, size_t workspace_bytes, void* stream) {
+size_t lsfa_mv_accumulate_trace_workspace_bytes(int N, int T, int height, int width) {
+  if (N <= 0 || T < 0 || height <= 0 || width <= 0) return 0;
+  return lsfa::mvacc_trace_workspace_bytes(N, T, height, width);
+}
+
+int lsfa_mv_accumulate_algo_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height, int width,
+                                int32_t* mv_out, void* workspace, size_t workspace_bytes, int algo, void* stream) {
   if (!mvs || !counts || !mv_out || !workspace) return fail(LSFA_E_BADARG, "NULL pointer");
+  if (algo < 0 || algo > 2) return fail(LSFA_E_BADARG, "algo must be 0 (auto), 1 (per-frame field) or 2 (cell-index back-trace)");
   if (N <= 0 || T < 0 || M <= 0 || height <= 0 || width <= 0 || N > 65535 || height > 65535 ||
       (long long)height * width >= (1LL << 31))
     return fail(LSFA_E_SHAPE, "bad dims (N and height index the launch grid: at most 65535; height*width < 2^31)");
-  if (workspace_bytes < lsfa_mv_accumulate_workspace_bytes(N, height, width))
-    return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", lsfa_mv_accumulate_workspace_bytes(N, height, width));
+  const size_t need_field = lsfa_mv_accumulate_workspace_bytes(N, height, width);
+  const size_t need_trace = (long long)N * T <= 65535 ? lsfa::mvacc_trace_workspace_bytes(N, T, height, width) : (size_t)-1;
+  const size_t need = algo == 1 ? need_field : (algo == 2 ? need_trace : (need_trace < need_field ? need_trace : need_field));
+  if (need == (size_t)-1) return fail(LSFA_E_UNSUPPORTED, "the back-trace form indexes its launch grid by N*T: at most 65535");
+  if (workspace_bytes < need) return fail(LSFA_E_BADARG, "workspace too small: need %zu bytes", need);
   if ((reinterpret_cast<uintptr_t>(workspace) % 8) || (reinterpret_cast<uintptr_t>(mv_out) % 8) ||
       (reinterpret_cast<uintptr_t>(mvs) % 8))
     return fail(LSFA_E_ALIGN, "mvs, workspace and mv_out must be 8-byte aligned");
-  return cuda_result(lsfa::launch_mv_accumulate(mvs, counts, N, T, M, height, width, mv_out, workspace, as_stream(stream)),
-                     "mv_accumulate launch");
+  cudaError_t e = lsfa::launch_mv_accumulate(mvs, counts, N, T, M, height, width, mv_out, workspace, workspace_bytes, algo, as_stream(stream));
+  if (e == cudaErrorNotSupported) {
+    cudaGetLastError();
+    return fail(LSFA_E_UNSUPPORTED, "the requested algorithm cannot serve these arguments (workspace size or N*T)");
+  }
+  return cuda_result(e, "mv_accumulate launch");
+}
+
+int lsfa_mv_accumulate_i32(const int32_t* mvs, const int32_t* counts, int N, int T, int M, int height, int width,
+                           int32_t* mv_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return lsfa_mv_accumulate_algo_i32(mvs, counts, N, T, M, height, width, mv_out, workspace, workspace_bytes, 0, stream);
 }
 
 int lsfa_coviar_residual_u8(const uint8_t* iframe, const uint8_t* cur, const int32_t* mv, int32_t* res, int N, int height,

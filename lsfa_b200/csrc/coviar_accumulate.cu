@@ -156,6 +156,124 @@ __global__ void coviar_residual_kernel(const unsigned char* __restrict__ iframe,
 }
 
 
+// ---------------------------------------------------------------------------------------------------------
+// Round 2: the back-trace without a per-frame field.  accu_t = accu_{t-1} o s_t with accu_0 = identity, so
+//     accu_T(p) = s_1(s_2(... s_T(p) ...)),   s_t(p) = p + (src - dst) of the LAST vector of frame t (list order) whose
+//                                              block covers p with p and its source inside the frame, else p:
+// a chain of T look-ups per pixel, walked from the target frame back to the I-frame.  "Which vector owns pixel p in frame
+// t" is answered from a CELL index instead of a per-pixel owner map: per 8x8 cell the largest index among the vectors
+// whose destination block touches the cell (one atomicMax per vector and touched cell: 57 KB per 720p frame, L2-resident).
+// Any vector covering p touches p's cell, so the owner's index is <= that maximum: the pixel tests the cell's top vector
+// first and walks down the list only if that one does not cover it (block-aligned streams - every real MPEG-4 stream -
+// never do: a 16x16 or 8x8 block on the 8-pixel grid covers its cells completely; frame borders and unaligned vectors do).
+// The accumulated field never crosses HBM: per GOP the traffic is the vector lists + the cell index + ONE write of the
+// result, instead of 2 reads + 1 write of the field and an owner-map round trip for every P-frame.  Bit-exact by
+// construction (the same three predicates as the reference's inner loop, coviar_data_loader.c:92-110).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCellShift = 3;   // 8x8 pixel cells
+
+// PASS 0: celltop[cell] = max index + 1 over the vectors touching the cell;  PASS 1: celltop2[cell] = the same over the
+// vectors below the cell's top one.  A pixel the top vector does not cover (the strip of a border block whose source
+// leaves the frame; a cell an unaligned block covers in part) then tries the second candidate - in block-aligned streams
+// there is none and the pixel is done - and only walks further down the list if that one fails too.
+template <int PASS>
+__global__ void mvacc_celltop_kernel(const MvRec* __restrict__ mvs, const int* __restrict__ counts, int* __restrict__ celltop,
+                                     int* __restrict__ celltop2, int T, int M, int height, int width, int cw, int ch) {
+  const int nt = blockIdx.y;                                     // n * T + t
+  const int cnt = min(__ldg(counts + nt), M);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const MvRec mv = mvs[(size_t)nt * M + i];
+  if (mv.dst_x - mv.src_x == 0 && mv.dst_y - mv.src_y == 0) return;      // :92
+  const int x_lo = (-1 * mv.w) / 2, x_hi = mv.w / 2, y_lo = (-1 * mv.h) / 2, y_hi = mv.h / 2;   // :97-98 (C division)
+  if (x_hi <= x_lo || y_hi <= y_lo) return;
+  const int x0 = max(mv.dst_x + x_lo, 0), x1 = min(mv.dst_x + x_hi - 1, width - 1);
+  const int y0 = max(mv.dst_y + y_lo, 0), y1 = min(mv.dst_y + y_hi - 1, height - 1);
+  if (x1 < x0 || y1 < y0) return;
+  int* ct = celltop + (size_t)nt * cw * ch;
+  int* ct2 = celltop2 + (size_t)nt * cw * ch;
+  for (int cy = y0 >> kCellShift; cy <= (y1 >> kCellShift); ++cy)
+    for (int cx = x0 >> kCellShift; cx <= (x1 >> kCellShift); ++cx) {
+      if (PASS == 0) atomicMax(ct + cy * cw + cx, i + 1);
+      else if (i + 1 < ct[cy * cw + cx]) atomicMax(ct2 + cy * cw + cx, i + 1);
+    }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256)
+mvacc_trace_kernel(const MvRec* __restrict__ mvs, const int* __restrict__ counts, const int* __restrict__ celltop,
+                   const int* __restrict__ celltop2, int2* __restrict__ mv_out, int T, int M, int height, int width, int cw, int ch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * ROWS, n = blockIdx.z;
+  if (x >= width) return;
+  int px[ROWS], py[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) { px[r] = x; py[r] = y0 + r; }
+  for (int t = T - 1; t >= 0; --t) {                             // from the target frame back to the I-frame
+    const int nt = n * T + t;
+    const int cnt = min(__ldg(counts + nt), M);
+    if (cnt == 0) continue;
+    const int* __restrict__ ct = celltop + (size_t)nt * cw * ch;
+    const int* __restrict__ ct2 = celltop2 + (size_t)nt * cw * ch;
+    const int2* __restrict__ list = reinterpret_cast<const int2*>(mvs + (size_t)nt * M);    // 3 x int2 per vector
+    int o[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)                               // the independent chains of this thread issue together
+      o[r] = (y0 + r < height) ? __ldg(ct + (py[r] >> kCellShift) * cw + (px[r] >> kCellShift)) : 0;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int cell = (py[r] >> kCellShift) * cw + (px[r] >> kCellShift);
+      int i = o[r] - 1;
+      bool first = true;
+      while (i >= 0) {                                           // almost always one iteration (see the header)
+        const int2 wh = __ldg(list + 3 * i), sr = __ldg(list + 3 * i + 1), ds = __ldg(list + 3 * i + 2);
+        const int xs = px[r] - ds.x, ys = py[r] - ds.y;          // offset inside the block: [-w/2, w/2) x [-h/2, h/2)
+        const int sx = sr.x + xs, sy = sr.y + ys;
+        if (!(ds.x - sr.x == 0 && ds.y - sr.y == 0) && xs >= (-1 * wh.x) / 2 && xs < wh.x / 2 && ys >= (-1 * wh.y) / 2 &&
+            ys < wh.y / 2 && (unsigned)sx < (unsigned)width && (unsigned)sy < (unsigned)height) {   // :92, :97-98, :105-108
+          px[r] = sx;
+          py[r] = sy;
+          break;
+        }
+        if (first) {                                             // the cell's second candidate, then down the list
+          first = false;
+          i = __ldg(ct2 + cell) - 1;
+        } else {
+          --i;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r)
+    if (y0 + r < height)                                         // :130-139: mv = (x,y) - accu
+      mv_out[((size_t)n * height + y0 + r) * width + x] = make_int2(x - px[r], y0 + r - py[r]);
+}
+
+size_t mvacc_trace_workspace_bytes(int N, int T, int height, int width) {
+  const size_t cw = (size_t)(width + 7) >> kCellShift, ch = (size_t)(height + 7) >> kCellShift;
+  return 2 * (size_t)N * (T > 0 ? T : 1) * cw * ch * sizeof(int);      // top + second candidate per cell
+}
+
+static cudaError_t run_mv_trace(const int* mvs, const int* counts, int N, int T, int M, int height, int width, int* mv_out,
+                                void* workspace, cudaStream_t st) {
+  const int cw = (width + 7) >> kCellShift, ch = (height + 7) >> kCellShift;
+  int* celltop = static_cast<int*>(workspace);
+  int* celltop2 = celltop + (size_t)N * (T > 0 ? T : 1) * cw * ch;
+  cudaError_t e = cudaMemsetAsync(celltop, 0, mvacc_trace_workspace_bytes(N, T, height, width), st);
+  if (e != cudaSuccess) return e;
+  if (T > 0) {
+    const dim3 grid((M + 127) / 128, N * T);
+    mvacc_celltop_kernel<0><<<grid, 128, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), counts, celltop, celltop2, T, M, height, width, cw, ch);
+    mvacc_celltop_kernel<1><<<grid, 128, 0, st>>>(reinterpret_cast<const MvRec*>(mvs), counts, celltop, celltop2, T, M, height, width, cw, ch);
+  }
+  // independent chains per thread: 1 row 1.88 ms, 2 rows 1.55, 4 rows 1.44, 8 rows 1.41 (64 GOPs x 11 P-frames at 720p; the
+  // per-frame field form: 2.86 ms) - the walk is instruction bound (~35 integer instructions per pixel and P-frame)
+  constexpr int ROWS = 4;
+  mvacc_trace_kernel<ROWS><<<dim3((width + 255) / 256, (height + ROWS - 1) / ROWS, N), 256, 0, st>>>(
+      reinterpret_cast<const MvRec*>(mvs), counts, celltop, celltop2, reinterpret_cast<int2*>(mv_out), T, M, height, width, cw, ch);
+  return cudaPeekAtLastError();
+}
+
 template <typename A>
 static cudaError_t run_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
                                      int* mv_out, void* workspace, cudaStream_t st) {
@@ -180,7 +298,12 @@ static cudaError_t run_mv_accumulate(const int* mvs, const int* counts, int N, i
 }
 
 cudaError_t launch_mv_accumulate(const int* mvs, const int* counts, int N, int T, int M, int height, int width,
-                                 int* mv_out, void* workspace, cudaStream_t st) {
+                                 int* mv_out, void* workspace, size_t workspace_bytes, int algo, cudaStream_t st) {
+  // algo: 0 auto, 1 the per-frame field form (round 1), 2 the cell-index back-trace (needs N*T*ceil(w/8)*ceil(h/8)*4 bytes)
+  const bool trace_fits = (long long)N * T <= 65535 && workspace_bytes >= mvacc_trace_workspace_bytes(N, T, height, width);
+  if (algo == 2 && !trace_fits) return cudaErrorNotSupported;
+  if (algo != 1 && trace_fits) return run_mv_trace(mvs, counts, N, T, M, height, width, mv_out, workspace, st);
+  if (workspace_bytes < (size_t)N * height * width * 20) return cudaErrorNotSupported;
   if (height <= 32767 && width <= 32767)
     return run_mv_accumulate<short2>(mvs, counts, N, T, M, height, width, mv_out, workspace, st);
   return run_mv_accumulate<int2>(mvs, counts, N, T, M, height, width, mv_out, workspace, st);

@@ -628,7 +628,10 @@ def unfused_chain(key, flow, scale_map, cur, logits, tmp=None) -> torch.Tensor:
     return out
 
 
-def mv_accumulate(mvs: torch.Tensor, counts: torch.Tensor, height: int, width: int, workspace=None) -> torch.Tensor:
+_MVACC_ALGO = {"auto": 0, "field": 1, "trace": 2}
+
+
+def mv_accumulate(mvs: torch.Tensor, counts: torch.Tensor, height: int, width: int, workspace=None, algo="auto") -> torch.Tensor:
     """coviar's accumulated MV field (coviar_data_loader.c:71-139, accumulate=1) for N GOPs at once.
     mvs (N,T,M,6) int32 {w,h,src_x,src_y,dst_x,dst_y} per P-frame in list order, counts (N,T) int32
     -> (N,height,width,2) int32, the array coviar_py2.load(video, gop, pos=T, 1, True) returns."""
@@ -642,8 +645,9 @@ def mv_accumulate(mvs: torch.Tensor, counts: torch.Tensor, height: int, width: i
     if workspace is None:
         workspace = torch.empty(need, dtype=torch.uint8, device=mvs.device)
     out = torch.empty((N, height, width, 2), dtype=torch.int32, device=mvs.device)
-    A.check(lib.lsfa_mv_accumulate_i32(mvs.data_ptr(), counts.data_ptr(), N, T, M, height, width, out.data_ptr(),
-                                       workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()))
+    A.check(lib.lsfa_mv_accumulate_algo_i32(mvs.data_ptr(), counts.data_ptr(), N, T, M, height, width, out.data_ptr(),
+                                            workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                            _MVACC_ALGO[algo], _stream()))
     return out
 
 

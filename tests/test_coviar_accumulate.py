@@ -50,8 +50,9 @@ def test_reconstruction_identity_of_the_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["auto", "field", "trace"])
 @pytest.mark.parametrize("N,T,h,w", [(1, 1, 32, 48), (3, 4, 48, 80), (2, 11, 96, 160), (2, 3, 45, 77)])
-def test_gpu_mv_accumulate_bit_exact(cuda, N, T, h, w):
+def test_gpu_mv_accumulate_bit_exact(cuda, N, T, h, w, algo):
     import torch
     from lsfa_b200 import ops
     rng = np.random.default_rng(N * 100 + T)
@@ -59,7 +60,7 @@ def test_gpu_mv_accumulate_bit_exact(cuda, N, T, h, w):
     mvs = np.stack([l[0] for l in lists]); counts = np.stack([l[1] for l in lists])
     counts[0, 0] = max(0, counts[0, 0] - 3)            # ragged counts
     want = np.stack([P.mv_accumulate(mvs[n], counts[n], h, w) for n in range(N)])
-    got = ops.mv_accumulate(torch.from_numpy(mvs).to(cuda), torch.from_numpy(counts).to(cuda), h, w)
+    got = ops.mv_accumulate(torch.from_numpy(mvs).to(cuda), torch.from_numpy(counts).to(cuda), h, w, algo=algo)
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
     iframe = rng.integers(0, 256, (N, h, w, 3), dtype=np.uint8)
@@ -93,3 +94,30 @@ def test_gpu_chain_from_motion_vector_lists_to_aggregated_feature(cuda):
                                    cur=t(cur), scale_map=t(sm), weight_mode="logits", logits=t(lg))
     torch.cuda.synchronize()
     assert_close_f32(got.cpu().numpy(), want, scale=max(np.abs(key).max(), np.abs(cur).max()), what="chain")
+
+
+@pytest.mark.gpu
+def test_gpu_back_trace_adversarial_lists(cuda):
+    """The cell-index back-trace on lists that defeat its fast path: unaligned blocks of odd sizes, vectors that overlap
+    earlier ones, static vectors (skipped, coviar_data_loader.c:92) sitting on top of moving ones, sources and
+    destinations leaving the frame on every side, an empty frame, and a frame that is not a multiple of the 8x8 cell."""
+    import torch
+    from lsfa_b200 import ops
+    rng = np.random.default_rng(99)
+    N, T, h, w, M = 3, 6, 53, 71, 90
+    mvs = np.zeros((N, T, M, 6), np.int32)
+    counts = np.full((N, T), M, np.int32)
+    for n in range(N):
+        for t in range(T):
+            for i in range(M):
+                bw, bh = (int(v) for v in rng.choice([3, 4, 5, 8, 15, 16, 17], 2))
+                dx, dy = int(rng.integers(-6, w + 6)), int(rng.integers(-6, h + 6))
+                ox, oy = (0, 0) if rng.random() < 0.25 else (int(v) for v in rng.integers(-20, 21, 2))
+                mvs[n, t, i] = (bw, bh, dx + ox, dy + oy, dx, dy)
+    counts[1, 2] = 0
+    counts[2, 4] = 7
+    want = np.stack([P.mv_accumulate(mvs[n], counts[n], h, w) for n in range(N)])
+    for algo in ("trace", "field"):
+        got = ops.mv_accumulate(torch.from_numpy(mvs).to(cuda), torch.from_numpy(counts).to(cuda), h, w, algo=algo)
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy(), want), algo

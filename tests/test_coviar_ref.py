@@ -65,6 +65,25 @@ def test_reference_library_live_against_fixture_and_oracle():
         assert np.array_equal(P.coviar_residual(iframe, cur, ref), R.residual(iframe, cur, mvs, counts))
 
 
+@pytest.mark.skipif(not R.available(), reason="neither /root/reference nor a prebuilt oracle/_ref")
+def test_reference_library_on_adversarial_lists():
+    """Unaligned blocks of odd sizes, static vectors on top of moving ones, sources / destinations outside the frame: the
+    C restatement still equals the compiled reference (these lists are what the GPU back-trace's slow path is tested on)."""
+    P.build()
+    rng = np.random.default_rng(98)
+    T, h, w, M = 5, 53, 71, 60
+    mvs = np.zeros((T, M, 6), np.int32)
+    for t in range(T):
+        for i in range(M):
+            bw, bh = (int(v) for v in rng.choice([3, 4, 5, 8, 15, 16, 17], 2))
+            dx, dy = int(rng.integers(-6, w + 6)), int(rng.integers(-6, h + 6))
+            ox, oy = (0, 0) if rng.random() < 0.25 else (int(v) for v in rng.integers(-20, 21, 2))
+            mvs[t, i] = (bw, bh, dx + ox, dy + oy, dx, dy)
+    counts = np.full(T, M, np.int32)
+    counts[2] = 0
+    assert np.array_equal(P.mv_accumulate(mvs, counts, h, w), R.mv_accumulate(mvs, counts, h, w))
+
+
 @pytest.mark.gpu
 def test_gpu_mv_accumulate_and_residual_equal_the_reference(cuda):
     import torch
@@ -88,6 +107,7 @@ def test_gpu_against_the_live_reference_library_at_720p(cuda):
     T, h, w = 11, 720, 1280
     mvs, counts = O.synth_mv_lists(rng, T, h, w, extra=16, max_disp=32)
     want = R.mv_accumulate(mvs, counts, h, w)
-    got = ops.mv_accumulate(torch.from_numpy(mvs[None]).to(cuda), torch.from_numpy(counts[None]).to(cuda), h, w)
-    torch.cuda.synchronize()
-    assert np.array_equal(got[0].cpu().numpy(), want)
+    for algo in ("trace", "field"):
+        got = ops.mv_accumulate(torch.from_numpy(mvs[None]).to(cuda), torch.from_numpy(counts[None]).to(cuda), h, w, algo=algo)
+        torch.cuda.synchronize()
+        assert np.array_equal(got[0].cpu().numpy(), want), algo

@@ -255,10 +255,15 @@ def upstream_rows(dev, pk, quick):
     mvs = mvs.reshape(Na, T, M, 6).contiguous()
     counts = torch.full((Na, T), M, dtype=torch.int32, device=dev)
     ws = torch.empty(Na * ha * wa * 20, dtype=torch.uint8, device=dev)
-    ms = time_ms(lambda: ops.mv_accumulate(mvs, counts, ha, wa, workspace=ws), 2, 5)
-    # algorithmic bytes per GOP: per P-frame read + write the (x,y) int2 field once, plus the vector list
+    # algorithmic bytes per GOP in the REFERENCE's formulation: per P-frame read + write the (x,y) int2 field once, plus the
+    # vector list; the back-trace form needs only the lists and one write of the result
     alg = T * (2 * ha * wa * 8 + M * 24) + ha * wa * 8
-    r = row("upstream: coviar MV accumulation, %d GOPs x 11 P-frames @720p" % Na, Na, alg, ms, pk, "unit = GOPs")
+    alg_trace = T * M * 24 + ha * wa * 8
+    ms = time_ms(lambda: ops.mv_accumulate(mvs, counts, ha, wa, workspace=ws, algo="field"), 2, 5)
+    row("upstream: coviar MV accumulation, per-frame field form (round 1), %d GOPs x 11 P-frames @720p" % Na, Na, alg, ms, pk, "unit = GOPs")
+    ms = time_ms(lambda: ops.mv_accumulate(mvs, counts, ha, wa, workspace=ws, algo="trace"), 2, 5)
+    row("upstream: coviar MV accumulation, cell-index back-trace, %d GOPs x 11 P-frames @720p (reference-formulation bytes)" % Na, Na, alg, ms, pk, "unit = GOPs")
+    r = row("upstream: coviar MV accumulation, cell-index back-trace (its own bytes: lists + one write of the field)", Na, alg_trace, ms, pk, "unit = GOPs")
     del mvs, counts, ws, off
 
 

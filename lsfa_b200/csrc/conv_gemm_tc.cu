@@ -107,6 +107,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, but naming the 32 registers a preceding tmem_ld32 filled as read-write operands: no instruction that reads
+// them can be scheduled above the wait (tcgen05.ld is asynchronous: its destinations are valid only after wait::ld)
+__device__ __forceinline__ void tmem_ld_wait_for(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major operand whose rows are 128 B (64 bf16) in the SWIZZLE_128B pattern the TMA
@@ -159,7 +171,9 @@ template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for SWIZZLE_128B; plain pointer arithmetic on the __shared__ array keeps the address space known
+  // to the compiler (an integer round trip made every bias / weight read a generic LD.E instead of LDS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [BN]
   float* s_w2t = s_bias + BN;                                                 // NQ: [BN][16] (transposed Nq_conv2 weight)
   float* s_nq = s_w2t + NQ_MID * BN;                                          // NQ: b2[16], w3[16], b3
@@ -273,36 +287,62 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
         for (int acc = 0; acc < n_acc; ++acc) {
           const int img = acc ? it.img1 : it.img0;
-          __nv_bfloat16* dst = P.out + (((size_t)img * P.H * P.W + pix) * P.Cout + (size_t)it.chunk * BN);
+          // 64 output channels (128 B of bf16) per step.  A thread owns a ROW of the accumulator, but rows are Cout*2 bytes
+          // apart in the output: storing from the row owner is 32 scattered 16-byte writes per instruction (ncu: the epilogue
+          // warps sat on the store queue and the tensor pipe idled 48 % of em_conv1).  So each warp transposes its 32 rows x
+          // 128 B through a 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row: conflict-free both ways) and stores
+          // with 8 lanes per row: four full 128-byte lines per instruction.
+          uint4* tile = reinterpret_cast<uint4*>(s_w2t) + ew * 256;          // [32 rows][8 chunks of 16 B]
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
+          for (int c0 = 0; c0 < BN; c0 += 64) {
+            float v[64];
             tmem_ld32(taddr + acc * BN + c0, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
+            tmem_ld32(taddr + acc * BN + c0 + 32, v + 32);
+            tmem_ld_wait_for(v);
+            tmem_ld_wait_for(v + 32);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = v[2 * j] + s_bias[c0 + 2 * j], b = v[2 * j + 1] + s_bias[c0 + 2 * j + 1];
-              if (EPI == EPI_STORE_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            if (valid) {
-              uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+            for (int q = 0; q < 8; ++q) {
+              uint32_t pk[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) d4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              for (int j = 0; j < 4; ++j) {
+                const int c = q * 8 + 2 * j;
+                float a = v[c] + s_bias[c0 + c], b = v[c + 1] + s_bias[c0 + c + 1];
+                if (EPI == EPI_STORE_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              tile[lane * 8 + (q ^ (lane & 7))] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = 4 * k + (lane >> 3), ch = lane & 7;              // row inside this warp's 32, 16-byte chunk
+              const uint4 val = tile[r * 8 + (ch ^ (r & 7))];
+              const int rr = ew * 32 + r;
+              const int xx = it.x0 + rr % P.BW, yy = it.y0 + rr / P.BW;
+              if (xx < P.W && yy < P.H)
+                *reinterpret_cast<uint4*>(P.out + (((size_t)img * P.H + yy) * P.W + xx) * P.Cout + (size_t)it.chunk * BN + c0 + ch * 8) = val;
+            }
+            __syncwarp();
           }
         }
       } else if (EPI == EPI_COSINE) {
         // acc0 = image b of Concat_0(conv_feat, warp_feat) = current-frame embedding, acc1 = warped one (SYM:133-138)
         float scc = 0.f, sww = 0.f, swc = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float ec[32], ewp[32];
-          tmem_ld32(taddr + c0, ec);
-          tmem_ld32(taddr + BN + c0, ewp);
-          tmem_ld_wait();
+        float bc[2][32], bw[2][32];
+        tmem_ld32(taddr, bc[0]);
+        tmem_ld32(taddr + BN, bw[0]);
+#pragma unroll 2
+        for (int i = 0; i < BN / 32; ++i) {
+          float* ec = bc[i & 1];
+          float* ewp = bw[i & 1];
+          tmem_ld_wait_for(ec);
+          tmem_ld_wait_for(ewp);
+          if (i + 1 < BN / 32) {
+            tmem_ld32(taddr + (i + 1) * 32, bc[(i + 1) & 1]);
+            tmem_ld32(taddr + BN + (i + 1) * 32, bw[(i + 1) & 1]);
+          }
+          const int c0 = i * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float b = s_bias[c0 + j];
@@ -326,11 +366,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float q[NQ_MID];
 #pragma unroll
           for (int j = 0; j < NQ_MID; ++j) q[j] = s_nq[j];                 // Nq_conv2 bias
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + acc * BN + c0, v);
-            tmem_ld_wait();
+          float buf[2][32];
+          tmem_ld32(taddr + acc * BN, buf[0]);
+#pragma unroll 2
+          for (int i = 0; i < BN / 32; ++i) {
+            float* v = buf[i & 1];
+            tmem_ld_wait_for(v);
+            if (i + 1 < BN / 32) tmem_ld32(taddr + acc * BN + (i + 1) * 32, buf[(i + 1) & 1]);
+            const int c0 = i * 32;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float a = fmaxf(v[c] + s_bias[c0 + c], 0.f);           // Nq_conv1 bias + ReLU (SYM:97-98)

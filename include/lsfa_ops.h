@@ -92,7 +92,8 @@ typedef struct LsfaAggArgs {
   int32_t layout;            /* LSFA_LAYOUT_* */
   int32_t N, C, H, W;        /* output frames, channels, output (= flow/grid) height, width */
   int32_t key_h, key_w;      /* spatial size of key planes; 0,0 = same as H,W */
-  int32_t num_keys;          /* number of key features behind `key` (for index checking); 0 = N */
+  int32_t num_keys;          /* number of key features behind `key`; 0 = N.  key_index values are CLAMPED into
+                                [0, num_keys) on the device (memory safety); the host path rejects bad slots */
 
   const void*    key;        /* (num_keys,C,key_h,key_w) | NHWC (num_keys,key_h,key_w,C) */
   const int32_t* key_index;  /* (N,) optional: which key feature frame n samples (tile_as.py:16-19) */

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
     r1 = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
     r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
   }
-  const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+  const int kn = key_slot(P, n);
   float T1 = 0.f, T2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
   const int c_begin = chunk * kTailCH, c_end = min(P.C, c_begin + kTailCH);
   for (int c = c_begin; c < c_end; ++c) {

@@ -45,7 +45,7 @@ agg_nchw_generic_kernel(const __grid_constant__ AggParams P) {
     r1 = __ldg(P.res + ((size_t)n * 3 + 1) * P.HW + p);
     r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
   }
-  const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+  const int kn = key_slot(P, n);
   for (int c = c_begin; c < c_end; ++c) {
     const float* __restrict__ plane = static_cast<const float*>(P.key) + ((size_t)kn * P.C + c) * P.HWk;
     const size_t e = ((size_t)n * P.C + c) * P.HW + p;
@@ -285,7 +285,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     // warp-only variant: the consumers store straight to global (measured 6-8 % faster: this variant is bound by
     // shared-memory bandwidth, and the staged form costs one STS plus one copy-engine read per element), so its
     // stages hold key planes only.  LSFA_TMA_STAGED_STORE=1 keeps the staged form (ablation).
-    const bool direct = var == kVarWarpOnly && getenv("LSFA_TMA_STAGED_STORE") == nullptr;
+    const bool direct = var == kVarWarpOnly && knob("LSFA_TMA_STAGED_STORE") == nullptr;
     const unsigned stage_bytes = direct ? off_scale : off_io + (io_bytes + 127u) / 128u * 128u;
     // (variants WITH a current feature keep the staged store: direct stores measured 168.2k -> 167.4k frames/s on the
     // headline and 167k -> 133k on the shared-key stream sweep, round 2)
@@ -312,12 +312,12 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
 
 cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
-  if (getenv("LSFA_TMA_STATIC")) P.sched = nullptr;          // experiment knobs (ablations)
-  if (getenv("LSFA_TMA_NO_RECORDS")) P.records = nullptr;
+  if (knob("LSFA_TMA_STATIC")) P.sched = nullptr;          // experiment knobs (ablations)
+  if (knob("LSFA_TMA_NO_RECORDS")) P.records = nullptr;
   {
     // share of the items handed out dynamically at the end (the rest is a static contiguous split)
     int pct = kTmaPoolPercent;
-    if (const char* e = getenv("LSFA_TMA_POOL_PCT")) pct = atoi(e);
+    if (const char* e = knob("LSFA_TMA_POOL_PCT")) pct = atoi(e);
     if (pct < 0) pct = 0;
     if (pct > 100) pct = 100;
     P.pool_base = P.items - P.items * pct / 100;
@@ -327,11 +327,11 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
   if (grid > P.items) grid = P.items;
   // planes cut into pixel parts: each part loads only the key rows its taps read (found by the pre-pass);
   // needs whole rows / planes to stay 16-byte addressable
-  const bool trim = P.sched && P.records && P.parts > 1 && (P.HWk % 4) == 0 && getenv("LSFA_NO_ROW_TRIM") == nullptr;
+  const bool trim = P.sched && P.records && P.parts > 1 && (P.HWk % 4) == 0 && knob("LSFA_NO_ROW_TRIM") == nullptr;
   P.rowrange = trim ? P.sched + (size_t)P.N * P.parts : nullptr;
   // small batches (the reference's batch-1 operating mode, BASELINE configs[0]): ONE cooperative launch - the kernel's own
   // consumers build the records before a grid-wide barrier; static work split, whole key planes: no pre-pass, no memset
-  P.coop = (P.records != nullptr && (long long)P.N * P.parts <= kCoopMaxVirtualFrames && getenv("LSFA_TMA_NO_COOP") == nullptr) ? 1 : 0;
+  P.coop = (P.records != nullptr && (long long)P.N * P.parts <= kCoopMaxVirtualFrames && knob("LSFA_TMA_NO_COOP") == nullptr) ? 1 : 0;
   if (P.coop) {
     P.sched = nullptr;
     P.rowrange = nullptr;

@@ -106,7 +106,7 @@ agg_nchw_plane_kernel(const __grid_constant__ AggParams P) {
       ++pc.n;
     }
     if (pit >= i1) return;
-    const int kn = P.key_index ? __ldg(P.key_index + pc.n) : pc.n;
+    const int kn = key_slot(P, pc.n);
     const float* src = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)pc.chunk * K) * P.HWk;
     if (pround >= 1) mbar_wait(&empty[ps], (unsigned)(pround - 1) & 1u);
     mbar_expect_tx(&full[ps], P.stage_bytes);

@@ -370,7 +370,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
         desc[s].y = chunk;
         mbar_expect_tx(&full[s], bytes);              // release: the descriptor is visible with the data
         if (!byp) {
-          const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+          const int kn = key_slot(P, n);
           const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)chunk * K) * P.HWk;
           if (!trimmed) {
             bulk_g2s(st, ksrc, P.key_bytes, &full[s]);

@@ -200,7 +200,7 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
         mbar_expect_tx(&full[s], bytes);
         if (rank == 0) {
           if (!cur_byp) {
-            const int kn = P.key_index ? __ldg(P.key_index + cur_n) : cur_n;
+            const int kn = key_slot(P, cur_n);
             const float* ksrc = static_cast<const float*>(P.key) + ((size_t)kn * P.C + (size_t)cur_chunk * K) * P.HWk;
             bulk_g2s_multicast(ring + (size_t)s * P.stage_bytes, ksrc, P.key_bytes, &full[s], (uint16_t)0x3);
           }

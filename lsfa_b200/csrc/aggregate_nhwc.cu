@@ -189,7 +189,7 @@ agg_nhwc_kernel(const __grid_constant__ AggParams P) {
       }
 
       if (x < P.W) {
-        const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+        const int kn = key_slot(P, n);
         const T* kbase = key + (size_t)kn * P.HWk * P.C + lane * L;
 #pragma unroll 1
         for (int r = 0; r < kTileH; ++r) {
@@ -397,7 +397,7 @@ cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaSt
     else if (!has_scale && has_cur && has_res) var = kVarResCur;
   }
   NtPlan Q;
-  const char* env = getenv("LSFA_NHWC_TMA");                    // ablation knob: LSFA_NHWC_TMA=0 keeps the LDG/STG kernel
+  const char* env = knob("LSFA_NHWC_TMA");                    // ablation knob: LSFA_NHWC_TMA=0 keeps the LDG/STG kernel
   bool want_tma = kernel == 3 || (kernel == 0 && !(env && env[0] == '0'));
   // bf16 blend variants on small batches: the two kernels are within 1-2 % at large batch, and the all-TMA kernel
   // pays ~12 us of ramp-up and tail per launch (measured: 64 frames of 1024x38x63 bf16 0.887 vs 0.919 of the peak for
@@ -406,7 +406,7 @@ cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaSt
       (long long)P.N * ((P.HW + 31) / 32) < 64LL * sms)
     want_tma = false;
   if (want_tma && plan_nhwc_tma(P, bf16, var, &Q)) {
-    if (getenv("LSFA_TMA_STATIC")) P.sched = nullptr;
+    if (knob("LSFA_TMA_STATIC")) P.sched = nullptr;
     if (P.sched) {                                              // one claim counter, zeroed per launch
       cudaError_t e = cudaMemsetAsync(P.sched, 0, sizeof(unsigned), st);
       if (e != cudaSuccess) return e;
@@ -426,7 +426,7 @@ cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaSt
   if (has_res) {
     const int cstep = 32 * (bf16 ? 8 : 4);
     const size_t need = (size_t)((P.C + cstep - 1) / cstep * cstep) * sizeof(float4);
-    if (need <= 40 * 1024 && getenv("LSFA_NHWC_RNET_GLOBAL") == nullptr) {
+    if (need <= 40 * 1024 && knob("LSFA_NHWC_RNET_GLOBAL") == nullptr) {
       dsm = need;
       P.rnet_smem = 1;
     }

@@ -214,7 +214,7 @@ agg_nhwc_tma_kernel(const __grid_constant__ AggParams P, const NtPlan Q) {
       if (npix_b < 0) break;
       const int n = hdr[rs].x, p0 = hdr[rs].y;
       const bool byp = hdr[rs].w != 0;
-      const int kn = P.key_index ? __ldg(P.key_index + n) : n;
+      const int kn = key_slot(P, n);
       const T* kbase = key + (size_t)kn * P.HWk * P.C;
       for (int g0 = 0; g0 < npix_b; g0 += G) {
         const int np = min(G, npix_b - g0);
@@ -450,21 +450,21 @@ inline bool plan_nhwc_tma(const AggParams& P, bool bf16, int var, NtPlan* Q) {
   if (g < 1) return false;
   int G = 1;
   while (G * 2 <= (int)g && G * 2 <= kNtMaxG) G *= 2;
-  if (const char* e = getenv("LSFA_NT_G")) {                   // experiment knob: smaller pixel groups, more stages
+  if (const char* e = knob("LSFA_NT_G")) {                   // experiment knob: smaller pixel groups, more stages
     const int want = atoi(e);
     while (G > 1 && G > want) G /= 2;
   }
   Q->G = G;
-  Q->merge_pairs = getenv("LSFA_NT_NO_MERGE") ? 0 : 1;
+  Q->merge_pairs = knob("LSFA_NT_NO_MERGE") ? 0 : 1;
   Q->groups = var == kVarResCur ? 1 : 2;
-  if (const char* e = getenv("LSFA_NT_GROUPS")) Q->groups = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = knob("LSFA_NT_GROUPS")) Q->groups = atoi(e) == 1 ? 1 : 2;
   Q->slot = (unsigned)slot;
   Q->off_scale = 4u * (unsigned)G * (unsigned)slot;
   Q->off_io = Q->off_scale + (has_scale ? (unsigned)G * (unsigned)slot : 0u);
   Q->stage_bytes = Q->off_io + (has_cur ? (unsigned)G * (unsigned)slot : 0u);
   int stages = (int)(kNtRingBudget / Q->stage_bytes);
   if (stages > kNtMaxStages) stages = kNtMaxStages;
-  if (const char* e = getenv("LSFA_NT_STAGES")) stages = max(2, min(stages, atoi(e)));
+  if (const char* e = knob("LSFA_NT_STAGES")) stages = max(2, min(stages, atoi(e)));
   stages -= stages % kNtStageMultiple;
   if (stages < kNtStageMultiple) return false;
   Q->stages = stages;

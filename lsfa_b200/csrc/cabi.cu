@@ -175,6 +175,7 @@ int build_params(const LsfaAggArgs* a, lsfa::AggParams& P) {
   P.N = a->N; P.C = a->C; P.H = a->H; P.W = a->W; P.HW = a->H * a->W;
   P.Hk = Hk; P.Wk = Wk; P.HWk = Hk * Wk;
   P.key = a->key; P.key_index = a->key_index;
+  P.num_keys = a->num_keys > 0 ? a->num_keys : a->N;
   P.flow_kind = a->flow_kind; P.flow = a->flow;
   P.mv_h = a->mv_h; P.mv_w = a->mv_w;
   P.mv_scale = a->im_scale * (1.0 / 16.0);      // image.py:224: scale = im_scale * rcnn_scale

@@ -8,6 +8,7 @@
 //  * mbar_* / bulk_g2s : mbarrier + cp.async.bulk (TMA bulk copy, SASS UBLKCP) wrappers.
 //  * ld/st helpers with cache hints for once-touched streams.
 #pragma once
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -17,6 +18,17 @@
 
 namespace lsfa {
 
+// Ablation / experiment knobs (work-split percentages, kernel-shape overrides ...) are COMPILED OUT of the product build:
+// the library's behaviour never depends on the environment.  Build with -DLSFA_EXPERIMENTS (LSFA_NVCC_EXTRA) to read them.
+inline const char* knob(const char* name) {
+#ifdef LSFA_EXPERIMENTS
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Kernel-side view of LsfaAggArgs (plain values, passed by value as a __grid_constant__)
 // ---------------------------------------------------------------------------------------
@@ -25,6 +37,7 @@ struct AggParams {
   int Hk, Wk, HWk;             // key plane dims
   const void* key;
   const int* key_index;
+  int num_keys;                // key features behind `key`: key_index values are clamped into [0, num_keys)
   int flow_kind;
   const void* flow;
   int mv_h, mv_w;
@@ -68,6 +81,14 @@ struct AggParams {
   unsigned* rowrange;          // 2 per (frame, pixel part), written by the pre-pass with atomicMax over zeros:
                                // [0] = last key row any tap of the part reads + 1, [1] = Hk - first such row; or NULL
 };
+
+// which key feature frame n samples (tile_as.py:16-19 without the tile).  A slot outside the table would make the
+// bulk copies read whole planes from an arbitrary address, so it is clamped (memory safety; the host entry points that see
+// the indices on the host - lsfa_host_aggregate_f32_nchw - reject them with an error instead)
+__device__ __forceinline__ int key_slot(const AggParams& P, int n) {
+  if (!P.key_index) return n;
+  return min(max(__ldg(P.key_index + n), 0), P.num_keys - 1);
+}
 
 // ---------------------------------------------------------------------------------------
 // a7: GridGenerator(warp)  -  grid = (flow + pos) / half - 1     (float32, add/div/sub)

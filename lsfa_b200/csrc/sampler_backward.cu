@@ -612,15 +612,18 @@ cudaError_t launch_sampler_backward(const float* data, const float* coords, int 
   P.half_w = half_w; P.half_h = half_h; P.wk_m1 = (float)(Wi - 1); P.hk_m1 = (float)(Hi - 1);
   const int sm_count = bwd_sm_count();
   cudaError_t e;
-  if (P.ggrid && !add_grid) {
-    e = cudaMemsetAsync(P.ggrid, 0, (size_t)P.N * 2 * P.HW * sizeof(float), st);
-    if (e != cudaSuccess) return e;
-  }
   size_t smem_main = 0, smem_lists = 0;
   int ppt = 5;
   const bool ws_ok = workspace && workspace_bytes >= bwd_workspace_bytes(P.N, P.HWk, P.HW) &&
                      (reinterpret_cast<uintptr_t>(workspace) % 16) == 0;
-  if (kernel != 1 && ws_ok && plan_bwd_gather(P, &smem_main, &smem_lists, &ppt)) {
+  // decide the kernel BEFORE touching any output: an unsupported request must leave the caller's buffers alone
+  const bool gather = kernel != 1 && ws_ok && plan_bwd_gather(P, &smem_main, &smem_lists, &ppt);
+  if (kernel == 2 && !gather) return cudaErrorNotSupported;
+  if (P.ggrid && !add_grid) {
+    e = cudaMemsetAsync(P.ggrid, 0, (size_t)P.N * 2 * P.HW * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (gather) {
     char* ws = static_cast<char*>(workspace);
     P.sched = reinterpret_cast<unsigned*>(ws);
     ws += r16((size_t)P.N * 4);
@@ -648,7 +651,7 @@ cudaError_t launch_sampler_backward(const float* data, const float* coords, int 
     if (grid > items) grid = items;
     {
       int pct = kTmaPoolPercent;
-      if (const char* e = getenv("LSFA_TMA_POOL_PCT")) pct = atoi(e);
+      if (const char* e = knob("LSFA_TMA_POOL_PCT")) pct = atoi(e);
       pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
       P.pool_base = items - items * pct / 100;
       P.pool_base -= P.pool_base % kTmaClaim;
@@ -664,7 +667,6 @@ cudaError_t launch_sampler_backward(const float* data, const float* coords, int 
     }
     return e;
   }
-  if (kernel == 2) return cudaErrorNotSupported;
   if (P.gdata && !P.add_data) {
     e = cudaMemsetAsync(P.gdata, 0, (size_t)P.N * P.C * P.HWk * sizeof(float), st);
     if (e != cudaSuccess) return e;

@@ -52,6 +52,13 @@ def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
         raise TypeError("%s must be a torch.Tensor, got %r" % (name, type(t)))
     if not t.is_cuda:
         raise ValueError("%s must live on a CUDA device (lsfa_b200 has no CPU path)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # the C library launches on the calling thread's CURRENT device and this wrapper enqueues on that device's
+        # current stream: a tensor of another device would be read through the wrong context (illegal address / silent
+        # peer access).  One host thread per GPU sets its device once (tester.py:301-309).
+        raise ValueError("%s lives on cuda:%d but the current device is cuda:%d: call torch.cuda.set_device(...) (or use "
+                         "`with torch.cuda.device(...)`) in the thread that drives this GPU"
+                         % (name, t.device.index, torch.cuda.current_device()))
     if dtype is not None and t.dtype != dtype:
         raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
     if not t.is_contiguous():

@@ -953,8 +953,8 @@ def test_torch_autograd_through_the_custom_ops(ops, cuda):
     assert_close_f32(host(tf.grad), want_f, scale=np.abs(want_f).max(), what="autograd grad_flow")
 
 
-@pytest.mark.parametrize("shape", [(3, 8, 68, 120), (2, 4, 100, 132), (4, 6, 60, 80)])
-def test_row_trimmed_key_loads_any_motion(ops, cuda, shape, monkeypatch):
+@pytest.mark.parametrize("shape", [(5, 8, 68, 120), (5, 4, 100, 132), (6, 6, 60, 80)])
+def test_row_trimmed_key_loads_any_motion(ops, cuda, shape):
     """Planes cut into pixel parts load only the key rows each part's taps read (row ranges from the record
     pre-pass).  Whatever the motion - huge flows, everything out of the plane, a still frame, bypass frames,
     a shared key - the result must be bit-identical to the untrimmed kernel and pass the oracle gate."""
@@ -970,9 +970,26 @@ def test_row_trimmed_key_loads_any_motion(ops, cuda, shape, monkeypatch):
     want = oracle_fused(d, O.W_LOGITS)
     got = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=3)
     assert_close_f32(host(got), want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="trimmed %s" % (shape,))
-    monkeypatch.setenv("LSFA_NO_ROW_TRIM", "1")
-    full = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=3)
+    full = run_fused(ops, cuda, d, "logits", "nchw", flow_kind="flow", force_generic=2)
     assert torch.equal(got, full)
+
+
+@pytest.mark.parametrize("variant", ["warp", "scale_cur", "res_cur"])
+@pytest.mark.parametrize("shape", [(10, 8, 38, 63), (10, 4, 68, 120)])
+def test_cooperative_one_launch_form_is_bit_identical(ops, cuda, variant, shape):
+    """Batches of up to 8 (frame, pixel part) pairs run as ONE cooperative launch (the kernel's own consumers build the
+    sampling records before a grid-wide barrier; BASELINE configs[0] is this mode); larger batches use the record pre-pass.
+    The same frames through both forms must agree bit for bit, and the launch accounting must say 1 vs 2."""
+    N, C, H, W = shape
+    d = make_case(700 + C, N, C, H, W, with_res=True, with_bypass=True)
+    kw = {"warp": dict(mode="none", use_scale=False), "scale_cur": dict(mode="logits", use_scale=True),
+          "res_cur": dict(mode="add", use_scale=False, use_res=True)}[variant]
+    big = run_fused(ops, cuda, d, kw["mode"], "nchw", use_scale=kw["use_scale"], use_res=kw.get("use_res", False), force_generic=3)
+    for lo in (0, 3, 7):
+        hi = lo + 3 if H * W <= 4320 else lo + 2        # <= 8 virtual frames
+        sub = {k: (v[lo:hi] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in d.items()}
+        small = run_fused(ops, cuda, sub, kw["mode"], "nchw", use_scale=kw["use_scale"], use_res=kw.get("use_res", False), force_generic=3)
+        assert torch.equal(small, big[lo:hi]), (variant, lo)
 
 
 def test_backward_golden_fixture_from_torch_autograd(ops, cuda):

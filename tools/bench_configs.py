@@ -268,6 +268,35 @@ def upstream_rows(dev, pk, quick):
 
 
 
+def motion_rows(dev, pk, quick):
+    """Shared-memory-bound variants under the two motion distributions: the synthetic i.i.d. per-macroblock vectors of
+    SURVEY 8d (half the blocks static, the rest uniform in [-32,32] px - neighbouring cells move independently: the worst
+    case for bank conflicts on the tap gathers) and vectors block-matched from the reference's demo video
+    (tests/golden/demo_block_mvs.npz, tools/make_demo_block_mvs.py: camera motion, neighbouring blocks move together)."""
+    import numpy as np
+    C, H, W, mvh, mvw = 1024, 38, 63, 600, 1000
+    HW, F4 = H * W, C * H * W * 4
+    N = 32 if quick else 64
+    d = synth(N, C, H, W, mvh, mvw, dev)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "demo_block_mvs.npz"))["block_mv"].astype(np.int32)
+    blk = torch.from_numpy(g[np.arange(N) % g.shape[0]]).to(dev)
+    demo = blk.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :mvh, :mvw].contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    nh = {k: ops.to_nhwc(d[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}
+    for tag, mv in (("synthetic i.i.d. blocks", d["mv"]), ("demo video (block matched)", demo)):
+        for name, alg, mk in (
+                ("V0 warp only, fp32 NCHW", 2 * F4 + 32 * HW, lambda: ops.PreparedAggregate(d["key"], mv, flow_kind="raw")),
+                ("V1 shipped non-key path (warp + rnet(res) + cur), fp32 NCHW", 3 * F4 + 44 * HW,
+                 lambda: ops.PreparedAggregate(d["key"], mv, flow_kind="raw", cur=d["cur"], res=d["res"], rnet_w=d["rnet_w"], rnet_b=d["rnet_b"], weight_mode="add")),
+                ("V2 headline (warp x scale, logits blend), fp32 NCHW", 4 * F4 + 40 * HW,
+                 lambda: ops.PreparedAggregate(d["key"], mv, flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"], weight_mode="logits", logits=d["logits"])),
+                ("V0 warp only, bf16 NHWC", F4 + 32 * HW, lambda: ops.PreparedAggregate(nh["key"], mv, flow_kind="raw", layout="nhwc_bf16")),
+                ("V1 shipped non-key path, bf16 NHWC", 3 * F4 // 2 + 44 * HW,
+                 lambda: ops.PreparedAggregate(nh["key"], mv, flow_kind="raw", cur=nh["cur"], res=d["res"], rnet_w=d["rnet_w"], rnet_b=d["rnet_b"], weight_mode="add", layout="nhwc_bf16"))):
+            p = mk()
+            row("motion = %s: %s" % (tag, name), N, alg, time_ms(lambda: p.run(s), 3, 20), pk)
+
+
 def keyframe_rows(dev, pk, quick):
     """Key-frame graphs end to end (SYM:468-477): K1 (lsfa warp x scale) -> embedding / Nq convolutions (LIBRARY GEMMs:
     cuDNN through torch, as north_star prescribes) -> K2 (lsfa cosine + blend).  Answers SURVEY 8f rank 2's question
@@ -347,6 +376,7 @@ def main():
     ap.add_argument("--only-nocur", action="store_true")
     ap.add_argument("--only-upstream", action="store_true")
     ap.add_argument("--only-keyframe", action="store_true")
+    ap.add_argument("--only-motion", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pk = peak()
@@ -355,6 +385,9 @@ def main():
         return
     if args.only_single:
         single_frame_rows(dev, pk)
+        return
+    if args.only_motion:
+        motion_rows(dev, pk, args.quick)
         return
     if args.only_keyframe:
         keyframe_rows(dev, pk, args.quick)

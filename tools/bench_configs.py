@@ -118,8 +118,28 @@ def single_frame_rows(dev, pk):
     p2s = ops.PreparedAggregate(d["key"], d["mv"], flow_kind="raw", cur=d["cur"], scale_map=d["scale_map"],
                                 weight_mode="logits", logits=d["logits"], workspace=False)
     row("single frame: fused V2, no scratch (1 launch)", 1, 4 * F4 + 40 * HW, time_ms(lambda: p2s.run(s), 10, 200), pk, "latency, eager")
+    # flow / grid given (the drop-in BilinearSampler): records are two coalesced loads per pixel
+    gridt = ops.GridGenerator(flow)
+    pf = ops.PreparedAggregate(d["key"], flow, flow_kind="flow")
+    row("single frame: fused warp, flow given (cooperative records)", 1, 2 * F4 + 8 * HW, time_ms(lambda: pf.run(s), 10, 200), pk, "latency, eager")
+    pfs = ops.PreparedAggregate(d["key"], flow, flow_kind="flow", workspace=False)
+    row("single frame: fused warp, flow given, records built inside every CTA (1 plain launch)", 1, 2 * F4 + 8 * HW,
+        time_ms(lambda: pfs.run(s), 10, 200), pk, "latency, eager")
+    pg = ops.PreparedAggregate(d["key"], gridt, flow_kind="grid")
+    pgs = ops.PreparedAggregate(d["key"], gridt, flow_kind="grid", workspace=False)
+
+    class _Chain:      # the three drop-in operators back to back (for the graph rows)
+        @staticmethod
+        def run(st):
+            with torch.cuda.stream(torch.cuda.ExternalStream(st)):
+                ops.BilinearSampler(d["key"], ops.GridGenerator(ops.mv_pool(d["mv"]), out=grid), out=out)
     for name, p, b in (("cfg1 single frame: fused warp, raw MV", p0, 2 * F4 + 32 * HW), ("single frame: fused V2", p2, 4 * F4 + 40 * HW),
-                       ("single frame: fused V2, no scratch", p2s, 4 * F4 + 40 * HW)):
+                       ("single frame: fused V2, no scratch", p2s, 4 * F4 + 40 * HW),
+                       ("single frame: fused warp, flow given (cooperative records)", pf, 2 * F4 + 8 * HW),
+                       ("single frame: fused warp, flow given, records inside every CTA", pfs, 2 * F4 + 8 * HW),
+                       ("single frame: BilinearSampler alone, grid given (cooperative)", pg, 2 * F4 + 8 * HW),
+                       ("single frame: BilinearSampler alone, grid given, records inside every CTA", pgs, 2 * F4 + 8 * HW),
+                       ("cfg1 single frame: mv_pool + GridGenerator + BilinearSampler (3 ops)", _Chain, 2 * F4 + 32 * HW)):
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for _ in range(3):

@@ -345,8 +345,9 @@ LSFA_API int lsfa_warp_backward_f32(const float* key, const float* flow, const f
  * Hand-written sm_100a implicit-GEMM convolutions (tcgen05.mma, fp32 accumulators in tensor memory, operands by
  * TMA tensor copies; lsfa_b200/csrc/conv_gemm_tc.cu).  Stated-tolerance variant: bf16 operands, fp32 accumulate
  * (the reference runs these convolutions in fp32 on cuDNN).  Activations are channels-last bf16 (NB,H,W,C);
- * NB must be even: the reference always convolves Concat_0 of two N-batches (SYM:95,133) and the kernel pairs
- * image b with image b + NB/2 on one weight tile.  Cin % 64 == 0, Cout % 256 == 0.
+ * The kernel pairs image b with image b + ceil(NB/2) on one weight tile (the reference always convolves Concat_0 of
+ * two N-batches, SYM:95,133); lsfa_conv_bf16_nhwc also takes an odd NB (one image is then computed twice), the two
+ * fused entry points need their 2N images.  Cin % 64 == 0, Cout % 256 == 0.
  *
  * weights: lsfa_pack_conv_weight_bf16 turns MXNet's (Cout,Cin,k,k) float32 into (Cout, k*k*Cin) bf16 (once per
  * parameter set).  bias stays float32. */

@@ -160,8 +160,11 @@ __device__ __forceinline__ Item decode_item(const ConvParams& P, int item) {
   int t = item / P.n_chunks;
   const int tile = t % (P.tiles_x * P.tiles_y);
   it.pair = t / (P.tiles_x * P.tiles_y);
-  it.img0 = it.pair + (it.which ? P.NB / 2 : 0);
-  it.img1 = it.pair + P.NB / 2;
+  // image b is paired with image b + ceil(NB/2); with an odd image count the last pair's partner is clamped to the last
+  // image (computed twice, stored twice with identical values) - only the plain STORE epilogues accept odd counts
+  const int half = (P.NB + 1) / 2;
+  it.img1 = min(it.pair + half, P.NB - 1);
+  it.img0 = it.which ? it.img1 : it.pair;
   it.x0 = (tile % P.tiles_x) * P.BW;
   it.y0 = (tile / P.tiles_x) * P.BH;
   return it;
@@ -354,7 +357,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (valid) {
           const size_t NP = (size_t)(P.NB / 2) * P.H * P.W;
-          float* dst = P.partial + (size_t)it.chunk * 3 * NP + (size_t)it.img0 * P.H * P.W + pix;
+          float* dst = P.partial + (size_t)it.chunk * 3 * NP + (size_t)it.pair * P.H * P.W + pix;
           dst[0] = scc;
           dst[NP] = sww;
           dst[2 * NP] = swc;
@@ -501,7 +504,8 @@ static const char* launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 }
 
 const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int sms, cudaStream_t stream) {
-  if (P.NB <= 0 || (P.NB & 1)) return "the tensor-core convolutions work on image pairs (Concat_0 of two N-batches): NB must be even";
+  if (P.NB <= 0) return "no images";
+  if ((P.NB & 1) && (epi == EPI_COSINE || epi == EPI_NQ)) return "the cosine / Nq epilogues pair image b with image b + N (Concat_0 of two N-batches): NB must be even";
   if (P.Cin % BK) return "Cin must be a multiple of 64";
   if (P.Cout % BN) return "Cout must be a multiple of 256";
   if (P.taps != 1 && P.taps != 9) return "kernel must be 1x1 or 3x3";
@@ -512,7 +516,7 @@ const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int
   P.n_chunks = P.Cout / BN;
   P.kc_per_tap = P.Cin / BK;
   P.k_steps = P.taps * P.kc_per_tap;
-  P.pair_items = (P.NB / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
+  P.pair_items = ((P.NB + 1) / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
   P.num_items = P.pair_items;
   if (epi != EPI_COSINE && 2 * P.pair_items <= sms) {   // fewer items than half the SMs: every tile on its own CTA
     P.num_items = 2 * P.pair_items;

@@ -122,3 +122,82 @@ def key_frame_nq(feat_key_old, flow, scale_map, conv_feat, nq_params, is_first_f
         q = nq_net(_lowp_input([warp, conv_feat], conv_dtype), *prepare_params(nq_params, conv_dtype)).float()
     logits = torch.cat([q[:n], q[n:]], dim=1).contiguous()                                                 # (N,2,H,W): [warp, conv]
     return ops.blend_logits(warp, conv_feat, logits, bypass=is_first_frame)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The non-key step with every graph switch of the reference (SYM:57-67, 209-272, 326-328, 570-586), in bf16 channels-last:
+# convolutions on this package's tensor-core kernels (ops.conv_bf16_nhwc), the warp / add through the fused operator, the
+# two tiny SE-block layers (1x1 convolutions on a (N,C,1,1) pooled vector) and the channel concat in torch.  The shipped
+# configuration is fuse_type='add', res_fuse='add', rnet_num_conv=0: that one is ops.cur_frame_path + ONE convolution.
+# BatchNorm variants (res_diff_bn, small_net_bn_before_fuse) are not built: they need running statistics the path does not own.
+# ------------------------------------------------------------------------------------------------------------------
+def _nhwc_bf16(x):
+    """(N,C,H,W) float32 -> (N,H,W,C) bf16 through this package's transpose kernel (C padded to a multiple of 64 with zeros
+    when needed: the 3-channel residual of res_diff_ada)."""
+    n, c, h, w = x.shape
+    if c % 64:
+        pad = torch.zeros((n, 64 - c % 64, h, w), dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], dim=1).contiguous()
+    return ops.to_nhwc(x.contiguous(), torch.bfloat16)
+
+
+def _conv(x_nhwc, wb, relu=False):
+    """mx.sym.Convolution (+ReLU) on tensor cores; wb = (weight (Cout,Cin,k,k) f32, bias (Cout,) f32) as MXNet holds them."""
+    w, b = wb
+    cin = x_nhwc.shape[3]
+    if w.shape[1] != cin:                                   # input channels were zero-padded to 64
+        w = torch.cat([w, torch.zeros((w.shape[0], cin - w.shape[1]) + tuple(w.shape[2:]), dtype=w.dtype, device=w.device)], dim=1)
+    return ops.conv_bf16_nhwc(x_nhwc, ops.pack_conv_weight(w.contiguous()), b.contiguous(), relu=relu)
+
+
+def _se(cat_nhwc, p1, p2):
+    """global average pool -> 1x1 conv + ReLU -> 1x1 conv + sigmoid (SYM:255-259, 266-270): (N,1,1,C') float32."""
+    s = cat_nhwc.float().mean(dim=(1, 2))                                    # (N, C)
+    s = torch.relu(s @ p1[0].reshape(p1[0].shape[0], -1).t() + p1[1])
+    return torch.sigmoid(s @ p2[0].reshape(p2[0].shape[0], -1).t() + p2[1])[:, None, None, :]
+
+
+def cur_frame_step(feat_key, motion_vector, res_diff, rnet_convs, cur_small, small_params, fuse_type="add", res_fuse="add",
+                   fuse_downsample=None, flow_kind="flow", im_scale=1.0) -> torch.Tensor:
+    """get_cur_test_symbol's tail (SYM:570-586) for every `small_net_fuse_type` (SYM:229-272), `rnet_num_conv`
+    (SYM:57-67) and `fuse_type` (SYM:323-328).  Inputs NCHW float32 as the reference holds them: feat_key (N,1024,H,W),
+    res_diff (N,3,H,W), cur_small (N,256,H,W); returns (N,H,W,1024) bf16 channels-last."""
+    key = _nhwc_bf16(feat_key)
+    x = _nhwc_bf16(res_diff)
+    for wb in rnet_convs[:-1]:
+        x = _conv(x, wb, relu=True)
+    rd = _conv(x, rnet_convs[-1])                                            # rnet_conv{num_conv}: 1x1 -> 1024
+    small = _nhwc_bf16(cur_small)
+    kw = dict(flow_kind=flow_kind, im_scale=im_scale, layout="nhwc_bf16")
+    if res_fuse == "add" and fuse_type in ("add", "addv2"):
+        # out = cur + (warp + res_diff): one fused pass - the convolved residual enters as the `cur` of an 'add', then the
+        # small-net branch is added the same way
+        if fuse_type == "add":
+            cur = _conv(small, small_params["fuse_reduce_add"])
+        else:
+            cur = _conv(_conv(small, small_params["fuse_reduce_add_conv1"], relu=True), small_params["fuse_reduce_add_conv2"])
+        cur = (cur.float() + rd.float()).to(torch.bfloat16)
+        return ops.warp_scale_aggregate(key, motion_vector, cur=cur, weight_mode="add", **kw)
+    if res_fuse == "add":
+        wp = ops.warp_scale_aggregate(key, motion_vector, cur=rd, weight_mode="add", **kw)
+    else:
+        wp = ops.warp_scale_aggregate(key, motion_vector, **kw)
+        wp = _conv(torch.cat([wp, rd], dim=3).contiguous(), fuse_downsample)
+    if fuse_type in ("add", "addv2"):
+        if fuse_type == "add":
+            cur = _conv(small, small_params["fuse_reduce_add"])
+        else:
+            cur = _conv(_conv(small, small_params["fuse_reduce_add_conv1"], relu=True), small_params["fuse_reduce_add_conv2"])
+        return (cur.float() + wp.float()).to(torch.bfloat16)
+    if fuse_type in ("concat", "concatv1"):
+        c1 = _conv(small, small_params["fuse_reduce_c1"])
+        c2 = _conv(wp, small_params["fuse_reduce_c2"])
+        cat = _conv(torch.cat([c2, c1], dim=3).contiguous(), small_params["fuse_reduce"], relu=(fuse_type == "concatv1"))
+        if fuse_type == "concat":
+            return cat
+        return (cat.float() * _se(cat, small_params["s_feat_conv1"], small_params["s_feat_conv2"]) + cat.float()).to(torch.bfloat16)
+    if fuse_type == "concatv2":
+        c = _conv(small, small_params["fuse_reduce_c1"])
+        sfeat = _se(torch.cat([wp, c], dim=3), small_params["s_feat_conv1"], small_params["s_feat_conv2"])
+        return (c.float() * sfeat + wp.float()).to(torch.bfloat16)
+    raise ValueError("unknown small_net_fuse_type %r" % (fuse_type,))

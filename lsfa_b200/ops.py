@@ -720,7 +720,7 @@ def _ksize(w_packed: torch.Tensor, Cin: int) -> int:
 
 def conv_bf16_nhwc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, relu: bool = False, out=None) -> torch.Tensor:
     """mx.sym.Convolution (stride 1, 'same' padding, with bias) [+ ReLU] on tensor cores: x (NB,H,W,Cin) bf16 channels-last,
-    w_packed from pack_conv_weight, bias (Cout,) f32 -> (NB,H,W,Cout) bf16.  NB even, Cin % 64 == 0, Cout % 256 == 0."""
+    w_packed from pack_conv_weight, bias (Cout,) f32 -> (NB,H,W,Cout) bf16.  Cin % 64 == 0, Cout % 256 == 0."""
     _dev(x, "x", torch.bfloat16)
     _dev(w_packed, "w_packed", torch.bfloat16)
     _dev(bias, "bias", torch.float32)

@@ -665,6 +665,65 @@ def warp_scale_aggregate_backward(out_grad, key, flow, cur=None, scale_map=None,
 
 
 # --------------------------------------------------------------------------------------
+# The graph switches around the non-key step that the shipped yaml does not select (SYM:57-67, 209-272, 326-328),
+# restated so that lsfa_b200.graphs.cur_frame_step can be checked for every one of them.  float64 convolutions.
+# --------------------------------------------------------------------------------------
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-np.asarray(x, F64)))
+
+
+def res_diff_ada(res_diff, convs):
+    """SYM:57-67 without BatchNorm: `convs` = [(w,b) 3x3 + ReLU] * rnet_num_conv + [(w,b) 1x1 -> 1024]."""
+    x = np.asarray(res_diff, F32)
+    for (w, b) in convs[:-1]:
+        x = np.maximum(conv2d(x, w, b, pad=1), 0)
+    w, b = convs[-1]
+    return conv2d(x, w, b)
+
+
+def fuse_small_net(warp_feat, cur_small, params, fuse_type):
+    """SYM:229-272 (no BatchNorm, no cur_scale): cur_small = the small net's feature (N,256,H,W)."""
+    wp = np.asarray(warp_feat, F32)
+    if fuse_type == "add":                                   # SYM:230-236 (shipped)
+        return conv2d(cur_small, *params["fuse_reduce_add"], pad=1) + wp
+    if fuse_type == "addv2":                                 # SYM:237-244
+        c = np.maximum(conv2d(cur_small, *params["fuse_reduce_add_conv1"], pad=1), 0)
+        return conv2d(c, *params["fuse_reduce_add_conv2"]) + wp
+    if fuse_type in ("concat", "concatv1"):                  # SYM:245-262
+        c1 = conv2d(cur_small, *params["fuse_reduce_c1"], pad=1)
+        c2 = conv2d(wp, *params["fuse_reduce_c2"], pad=1)
+        cat = conv2d(np.concatenate([c2, c1], axis=1), *params["fuse_reduce"], pad=1)
+        if fuse_type == "concat":
+            return cat
+        cat = np.maximum(cat, 0)
+        sfeat = cat.mean(axis=(2, 3), keepdims=True, dtype=F64).astype(F32)
+        sfeat = np.maximum(conv2d(sfeat, *params["s_feat_conv1"]), 0)
+        sfeat = _sigmoid(conv2d(sfeat, *params["s_feat_conv2"])).astype(F32)
+        return cat * sfeat + cat
+    if fuse_type == "concatv2":                              # SYM:263-272
+        c = conv2d(cur_small, *params["fuse_reduce_c1"], pad=1)
+        cat = np.concatenate([wp, c], axis=1)
+        sfeat = cat.mean(axis=(2, 3), keepdims=True, dtype=F64).astype(F32)
+        sfeat = np.maximum(conv2d(sfeat, *params["s_feat_conv1"]), 0)
+        sfeat = _sigmoid(conv2d(sfeat, *params["s_feat_conv2"])).astype(F32)
+        return c * sfeat + wp
+    raise ValueError(fuse_type)
+
+
+def cur_frame_step(feat_key, flow, res_diff, rnet_convs, cur_small, small_params, fuse_type="add", res_fuse="add",
+                   fuse_downsample=None):
+    """get_cur_test_symbol's tail (SYM:570-586) with every switch: warp(key, MV); res_diff_ada; fuse_type 'add' | 'concat'
+    (SYM:326-328: 1x1 conv over Concat_1(warp, res_diff)); fuse_small_net."""
+    wp = warp(feat_key, flow)
+    rd = res_diff_ada(res_diff, rnet_convs)
+    if res_fuse == "add":
+        wp = wp + rd
+    else:
+        wp = conv2d(np.concatenate([wp, rd], axis=1), *fuse_downsample)
+    return fuse_small_net(wp, cur_small, small_params, fuse_type)
+
+
+# --------------------------------------------------------------------------------------
 # Stated-tolerance bf16 variant of the two networks (the tensor-core kernels of SURVEY 8f rank 2):
 # same graphs as embed_net / nq_net above with the product's rounding points made explicit -
 # inputs, convolution weights and the two hidden activations of the embedding net are rounded to

@@ -45,7 +45,8 @@ def conv_ref_f64(x, w, b, pad, relu):
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,k", [
     (2, 38, 63, 128, 256, 1), (2, 38, 63, 64, 256, 3), (4, 7, 9, 64, 512, 3), (2, 68, 120, 64, 256, 1),
-    (2, 5, 130, 64, 256, 3), (6, 17, 23, 192, 256, 3), (2, 1, 1, 64, 256, 3)])
+    (2, 5, 130, 64, 256, 3), (6, 17, 23, 192, 256, 3), (2, 1, 1, 64, 256, 3), (1, 12, 14, 64, 256, 3), (5, 17, 23, 64, 512, 1),
+    (11, 38, 63, 64, 256, 3)])
 def test_conv_bf16_nhwc_matches_float64_conv(ops, cuda, NB, H, W, Cin, Cout, k, relu):
     rng = np.random.default_rng(NB * 1000 + H * 10 + k)
     x = O.bf16_round(O.synth_features(rng, (NB, Cin, H, W)))
@@ -181,14 +182,48 @@ def test_key_frame_graphs_on_tensor_cores_against_fp32_oracle(ops, cuda):
 
 def test_tc_errors_are_loud(ops, cuda):
     from lsfa_b200 import LsfaError
-    x = torch.zeros((3, 4, 4, 64), dtype=torch.bfloat16, device=cuda)          # odd number of images
-    w = torch.zeros((256, 64), dtype=torch.bfloat16, device=cuda)
     b = torch.zeros(256, device=cuda)
-    with pytest.raises(LsfaError):
-        ops.conv_bf16_nhwc(x, w, b)
+    z = lambda *sh, dt=torch.float32: torch.zeros(sh, dtype=dt, device=cuda)  # noqa: E731
+    with pytest.raises(ValueError):                                             # the fused entries need Concat_0 of two batches
+        ops.nq_logits(z(3, 4, 4, 64, dt=torch.bfloat16), (z(256, 576, dt=torch.bfloat16), z(256), z(16, 256), z(16), z(16), z(1)))
     x = torch.zeros((2, 4, 4, 32), dtype=torch.bfloat16, device=cuda)          # Cin not a multiple of 64
     with pytest.raises(LsfaError):
         ops.conv_bf16_nhwc(x, torch.zeros((256, 32), dtype=torch.bfloat16, device=cuda), b)
     x = torch.zeros((2, 4, 4, 64), dtype=torch.bfloat16, device=cuda)          # Cout not a multiple of 256
     with pytest.raises(LsfaError):
         ops.conv_bf16_nhwc(x, torch.zeros((128, 64), dtype=torch.bfloat16, device=cuda), torch.zeros(128, device=cuda))
+
+
+@pytest.mark.parametrize("fuse_type", ["add", "addv2", "concat", "concatv1", "concatv2"])
+@pytest.mark.parametrize("rnet_num_conv,res_fuse", [(0, "add"), (1, "add"), (0, "concat")])
+def test_non_key_step_with_every_graph_switch(ops, cuda, fuse_type, rnet_num_conv, res_fuse):
+    """get_cur_test_symbol's tail (SYM:570-586) with the switches the shipped yaml does not select: small_net_fuse_type
+    addv2 / concat / concatv1 / concatv2 (SYM:237-272), rnet_num_conv > 0 (SYM:62-64), fuse_type 'concat' (SYM:326-328) -
+    bf16 tensor-core convolutions + the fused warp against the float64-convolution oracle, 2e-2 * max|out| (several
+    bf16-rounded layers deep)."""
+    from lsfa_b200 import graphs
+    rng = np.random.default_rng(len(fuse_type) * 10 + rnet_num_conv)
+    N, C, H, W, NF = 3, 256, 10, 13, 64                  # C stands in for 1024, NF for the small net's 256
+    mk = lambda co, ci, k: ((rng.standard_normal((co, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32),  # noqa: E731
+                            (0.1 * rng.standard_normal(co)).astype(np.float32))
+    key = O.synth_features(rng, (N, C, H, W))
+    flow = (rng.standard_normal((N, 2, H, W)) * 1.5).astype(np.float32)
+    res = (rng.standard_normal((N, 3, H, W)) * 2).astype(np.float32)
+    small = O.synth_features(rng, (N, NF, H, W))
+    rnet = ([mk(256, 3, 3)] if rnet_num_conv else []) + [mk(C, 256 if rnet_num_conv else 3, 1)]
+    sp = {"fuse_reduce_add": mk(C, NF, 3), "fuse_reduce_add_conv1": mk(256, NF, 3), "fuse_reduce_add_conv2": mk(C, 256, 1),
+          "fuse_reduce_c1": mk(C if fuse_type == "concatv2" else 256, NF, 3), "fuse_reduce_c2": mk(256, C, 3), "fuse_reduce": mk(C, 512, 3),
+          "s_feat_conv1": mk(C, 2 * C if fuse_type == "concatv2" else C, 1), "s_feat_conv2": mk(C, C, 1)}
+    if fuse_type == "addv2":
+        small = O.synth_features(rng, (N, 256, H, W))    # addv2 keeps the small net's width in its first convolution
+        sp["fuse_reduce_add_conv1"] = mk(256, 256, 3)
+    down = mk(C, 2 * C, 1)
+    want = O.cur_frame_step(key, flow, res, rnet, small, sp, fuse_type, res_fuse, down)
+    t = lambda a: dev(a, cuda)  # noqa: E731
+    tp = lambda wb: (t(wb[0]), t(wb[1]))  # noqa: E731
+    got = graphs.cur_frame_step(t(key), t(flow), t(res), [tp(x) for x in rnet], t(small), {k: tp(v) for k, v in sp.items()},
+                                fuse_type, res_fuse, tp(down))
+    torch.cuda.synchronize()
+    got = got.float().permute(0, 3, 1, 2).cpu().numpy()
+    err = np.abs(got - want)
+    assert err.max() <= 2e-2 * np.abs(want).max(), "%s/%s: worst abs err %.3g at scale %.3g" % (fuse_type, res_fuse, err.max(), np.abs(want).max())

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) agg_records_kernel(const __grid_constant_
     if (P.bypass != nullptr && __ldg(P.bypass + n) != 0) continue;   // never read for bypass frames
     const int y = p / P.W, x = p - y * P.W;
     const PixelLoads ld = issue_pixel_loads(P, n, y, x);
-    const PixelRec t = finish_pixel(P, ld, n, y, x);
+    PixelRec t = finish_pixel(P, ld, n, y, x);
+    if (P.canon) canonical_taps(t, P.Hk, P.Wk);
     uint4 a, b;
     pack_record(t, a, b);
     rec[2 * i] = a;
@@ -252,6 +253,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   const int var = variant_of(P);
   if (var == kVarRuntime) return false;
   if (P.HWk > 16383) return false;                               // tap byte offsets are packed in 16 bits
+  if (P.Hk < 2 || P.Wk < 2) return false;                        // canonical_taps(): a 2x2 block inside the plane
   const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
   for (const void* q : ptrs)
     if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
@@ -274,7 +276,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   const size_t res_bytes = var == kVarResCur ? (ppt <= 5 ? 0 : (size_t)3 * part_pix * 4) + (size_t)P.C * 16 : 0;
   const int io_plane = parts == 1 ? P.HW : part_pix;             // elements per plane slice in a stage
   const size_t pad = (((size_t)part_pix - (parts == 1 ? P.HW : 0)) * 4 + 127) / 128 * 128;
-  const int prefer[2] = {2, 1};
+  const int prefer[2] = {2, 1};   // (four planes per item measured slower on the warp-only variant: 0.79 -> 0.74)
   for (int i = 0; i < 2; ++i) {
     const int K = prefer[i];
     if (P.C % K) continue;
@@ -284,15 +286,15 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
     const unsigned off_io = has_scale ? off_scale + (io_bytes + 127u) / 128u * 128u : off_scale;
     // warp-only variant: the consumers store straight to global (measured 6-8 % faster: this variant is bound by
     // shared-memory bandwidth, and the staged form costs one STS plus one copy-engine read per element), so its
-    // stages hold key planes only.  LSFA_TMA_STAGED_STORE=1 keeps the staged form (ablation).
-    const bool direct = var == kVarWarpOnly && knob("LSFA_TMA_STAGED_STORE") == nullptr;
+    // stages hold key planes only.
+    const bool direct = var == kVarWarpOnly;                     // compile-time in the kernel (tma_consumer_loop<.., DIRECT>)
     const unsigned stage_bytes = direct ? off_scale : off_io + (io_bytes + 127u) / 128u * 128u;
     // (variants WITH a current feature keep the staged store: direct stores measured 168.2k -> 167.4k frames/s on the
     // headline and 167k -> 133k on the shared-key stream sweep, round 2)
     P.direct_store = direct ? 1 : 0;
     long long stages = ((long long)kSmemMax - kTmaHeaderBytes - (long long)res_bytes - (long long)pad) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 3 && !(i == 1 && stages >= 2)) continue;    // want >= 3 stages; K=1 may run with 2
+    if (stages < 3 && !(K == 1 && stages >= 2)) continue;    // want >= 3 stages; K=1 may run with 2
     P.K = K;
     P.chunks = P.C / K;
     P.parts = parts;
@@ -312,6 +314,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
 
 cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
+  P.canon = 1;
   if (knob("LSFA_TMA_STATIC")) P.sched = nullptr;          // experiment knobs (ablations)
   if (knob("LSFA_TMA_NO_RECORDS")) P.records = nullptr;
   {
@@ -362,7 +365,7 @@ bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
   const size_t kSmemMax = 227 * 1024;
   const int var = variant_of(P);
   if (var == kVarRuntime) return false;
-  if (P.HWk > 16383 || (P.HW % 4) || (P.HWk % 4)) return false;
+  if (P.HWk > 16383 || (P.HW % 4) || (P.HWk % 4) || P.Hk < 2 || P.Wk < 2) return false;
   const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
   for (const void* q : ptrs)
     if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
@@ -401,6 +404,7 @@ bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
 
 cudaError_t launch_agg_nchw_tma2(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
+  P.canon = 1;
   long long clusters = sm_count() / 2;
   if (clusters > P.items) clusters = P.items;
   if (P.sched) {

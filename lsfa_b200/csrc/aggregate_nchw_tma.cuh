@@ -47,7 +47,7 @@ constexpr int kCoopMaxVirtualFrames = 8;   // up to this many (frame, pixel part
 // work on the stages the producer warp fills.  fixed_part < 0: the stage descriptor carries a virtual
 // frame (frame * parts + part); fixed_part >= 0 (cluster kernel): it carries the frame, and this CTA
 // always works on pixel part `fixed_part`.
-template <int K, int PPT, int VAR>
+template <int K, int PPT, int VAR, bool DIRECT>
 __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* full, uint64_t* done, volatile int2* desc,
                                                   unsigned char* ring, float* res_s, float4* rnet_s, const int tid,
                                                   const int fixed_part) {
@@ -57,13 +57,14 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
   const bool has_bypass = P.bypass != nullptr;
   // ================================= consumer warps ==========================================
   float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
-  unsigned o_top[PPT], o_bot[PPT];
+  unsigned ob[PPT];                    // byte offset of the 2x2 tap block inside a key plane (canonical_taps)
   unsigned valid = 0;
   int cur_vf = -1, n = 0;
   bool byp = false;
   int s = 0;
   unsigned ph = 0;
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
+  const unsigned row_bytes = (unsigned)P.Wk * 4u;
   const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
   (void)ww;
   constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
@@ -123,7 +124,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           w00[j] = __uint_as_float(ra[j].x); w01[j] = __uint_as_float(ra[j].y);
           w10[j] = __uint_as_float(ra[j].z); w11[j] = __uint_as_float(ra[j].w);
           wc[j] = __uint_as_float(rb[j].x); ww[j] = __uint_as_float(rb[j].y);
-          o_top[j] = rb[j].z; o_bot[j] = rb[j].w;
+          ob[j] = rb[j].z & 0xffffu;
           if (has_res) {
             const int p = pix0 + tid + j * kTmaConsumers;
             if (p < pend && !byp) {
@@ -145,7 +146,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
-        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
+        ob[j] = 0u;                    // slot outside the part: taps read offset 0, store is predicated off
       }
       // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
       if (!byp) {
@@ -175,11 +176,11 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           if (p < pend) {
             valid |= 1u << j;
             if (!byp) {
-              const PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
+              PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
+              canonical_taps(t, P.Hk, P.Wk);
               w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
               wc[j] = t.wc; ww[j] = t.ww;
-              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
-              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
+              ob[j] = (unsigned)(t.i00 * 4);
               if (has_res) {
                 if (RES_REG) {
                   rr0[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
@@ -203,7 +204,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
       const int c0 = chunk * K;
       // variants without a current feature may skip the shared-memory staging of the output (one STS and one
       // copy-engine read per element less on the variants that are shared-memory-bandwidth bound)
-      const bool direct = !has_cur && P.direct_store != 0;
+      constexpr bool direct = DIRECT;
       float* out_g = nullptr;
       if (direct) {
         const int part_d = fixed_part >= 0 ? fixed_part : cur_vf - n * P.parts;
@@ -226,13 +227,15 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           for (int g = 0; g < JG; ++g) {   // all shared-memory reads of the group first ...
             const int j = j0 + g;
             if (j < PPT) {
-              v00[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
-              v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
-              v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
-              v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
-              const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written
-              sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
-              cu[g] = (has_cur && ok) ? io_s[j * kTmaConsumers] : 0.0f;
+              const unsigned char* top = plane_s + ob[j];          // the 2x2 block: two adds, four loads at +0 / +4
+              const unsigned char* bot = top + row_bytes;
+              v00[g] = *reinterpret_cast<const float*>(top);
+              v01[g] = *reinterpret_cast<const float*>(top + 4);
+              v10[g] = *reinterpret_cast<const float*>(bot);
+              v11[g] = *reinterpret_cast<const float*>(bot + 4);
+              // slots past the plane read the stage's tail padding (allocated, see plan_tma_kernel) and are not written
+              sc[g] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;
+              cu[g] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
             }
           }
 #pragma unroll
@@ -433,7 +436,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       if (P.coop) cooperative_groups::this_grid().sync();
       int s = 0;
       unsigned ph = 0;
-      const bool direct = !has_cur && P.direct_store != 0;   // the consumers wrote the output themselves
+      constexpr bool direct = VAR == kVarWarpOnly;           // the consumers wrote the output themselves
       while (live > 0) {
         mbar_wait(&done[s], ph);                       // consumers finished this stage; out is in smem
         if (!direct) issue_store(s);
@@ -469,7 +472,8 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       if (has_bypass && __ldg(P.bypass + n) != 0) continue;
       const int y = p / P.W, x = p - y * P.W;
       const PixelLoads ld = issue_pixel_loads(P, n, y, x);
-      const PixelRec t = finish_pixel(P, ld, n, y, x);
+      PixelRec t = finish_pixel(P, ld, n, y, x);
+      canonical_taps(t, P.Hk, P.Wk);
       uint4 a, b;
       pack_record(t, a, b);
       __stcg(rec + 2 * i, a);
@@ -478,7 +482,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
     __threadfence();
     cooperative_groups::this_grid().sync();
   }
-  tma_consumer_loop<K, PPT, VAR>(P, full, done, desc, ring, res_s, rnet_s, tid, -1);
+  tma_consumer_loop<K, PPT, VAR, VAR == kVarWarpOnly>(P, full, done, desc, ring, res_s, rnet_s, tid, -1);
 }
 
 template <int VAR>

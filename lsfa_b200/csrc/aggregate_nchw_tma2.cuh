@@ -247,7 +247,7 @@ agg_nchw_tma2_kernel(const __grid_constant__ AggParams P) {
       bulk_wait_all();
     }
   } else {
-    tma_consumer_loop<K, PPT, VAR>(P, full, done, desc, ring, res_s, rnet_s, tid, (int)rank);
+    tma_consumer_loop<K, PPT, VAR, false>(P, full, done, desc, ring, res_s, rnet_s, tid, (int)rank);
   }
   cluster_sync_all();   // neither CTA leaves while the other may still signal or multicast into it
 }

@@ -676,7 +676,7 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 size_t lsfa_embed_cosine_logits_workspace_bytes(int N, int H, int W, int C1, int C2, int E) {
   if (N <= 0 || H <= 0 || W <= 0 || C1 <= 0 || C2 <= 0 || E <= 0) return 0;
   const size_t px = (size_t)2 * N * H * W;
-  return align256(px * C1 * 2) + align256(px * C2 * 2) + align256((size_t)(E / 256) * 3 * N * H * W * 4);
+  return align256(px * C1 * 2) + align256(px * C2 * 2) + align256((size_t)(E / 256) * 2 * 3 * N * H * W * 4);
 }
 
 int lsfa_embed_cosine_logits_bf16_nhwc(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
@@ -706,7 +706,7 @@ int lsfa_embed_cosine_logits_bf16_nhwc(const void* x, const void* w1, const floa
   // em_conv3 (SYM:127-128) with compute_weight's reductions (SYM:111-116) as its epilogue
   P.Cin = C2; P.Cout = E; P.taps = 1; P.bias = b3; P.out = nullptr; P.partial = partial;
   if (int r = tc_result(lsfa::tc::launch_conv(h2, w3, P, lsfa::tc::EPI_COSINE, sms, st), "em_conv3+cosine")) return r;
-  lsfa::tc::launch_cosine_finalize(partial, logits, E / 256, N, H * W, st);
+  lsfa::tc::launch_cosine_finalize(partial, logits, 2 * (E / 256), N, H * W, st);   // two column halves per 256-channel chunk
   return cuda_result(cudaPeekAtLastError(), "cosine finalize launch");
 }
 

@@ -46,9 +46,14 @@ constexpr int A_BYTES = BM * BK * 2;    // 16 KB
 constexpr int B_BYTES = BN * BK * 2;    // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;   // 64 KB
 constexpr int NQ_MID = 16;              // Nq_conv2 width (SYM:99)
-constexpr int EPI_SMEM_FLOATS = BN + NQ_MID * BN + 3 * NQ_MID + 16;
+constexpr int EPI_WARPS = 8;            // two epilogue warps per tensor-memory lane quarter (see the epilogue)
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_TILE_FLOATS = EPI_WARPS * 1024;    // STORE: a 4 KB transpose tile per epilogue warp (NQ: the 16 x 256 tail weights)
+constexpr int EPI_SMEM_FLOATS = BN + EPI_TILE_FLOATS + 3 * NQ_MID + 16;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 128 /*barriers*/;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 128 + EPI_THREADS;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(NQ_MID * BN <= EPI_TILE_FLOATS, "Nq tail weights share the transpose tiles' space");
 constexpr int TMEM_COLS = 512;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -119,7 +124,7 @@ __device__ __forceinline__ void tmem_ld_wait_for(float* v) {
                :
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // shared-memory matrix descriptor, K-major operand whose rows are 128 B (64 bf16) in the SWIZZLE_128B pattern the TMA
 // wrote: 8-row atoms of 1024 B, stride between atoms (SBO) 1024 B, LBO unused for swizzled K-major; version 1 (sm_100).
@@ -179,7 +184,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [BN]
   float* s_w2t = s_bias + BN;                                                 // NQ: [BN][16] (transposed Nq_conv2 weight)
-  float* s_nq = s_w2t + NQ_MID * BN;                                          // NQ: b2[16], w3[16], b3
+  float* s_nq = s_w2t + EPI_TILE_FLOATS;                                          // NQ: b2[16], w3[16], b3
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4);
   uint64_t* full = bars;                    // [STAGES] TMA -> MMA
   uint64_t* empty = bars + STAGES;          // [STAGES] MMA -> TMA
@@ -200,13 +205,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    mbar_init(tmem_empty, EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   if (EPI == EPI_NQ && warp >= 4) {          // the per-pixel tail's parameters: once per CTA
     const int t = threadIdx.x - 128;
-    for (int i = t; i < NQ_MID * BN; i += 128) {
+    for (int i = t; i < NQ_MID * BN; i += EPI_THREADS) {
       const int j = i / BN, c = i % BN;       // global (16, 256) row-major -> smem [c][j]
       s_w2t[c * NQ_MID + j] = P.nq_w2[i];
     }
@@ -271,16 +276,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: thread r owns accumulator row r =====================
-    const int ew = warp - 4;                       // == warp % 4: the tensor-memory lane quarter this warp may read
+    // EIGHT epilogue warps: warp w may read tensor-memory lanes 32*(w % 4)..+31, so warps 4-7 and 8-11 cover the four
+    // quarters twice.  The epilogue is latency bound (clock64 trace: 1,365 cycles per 64-column step for ~300 instructions
+    // with ONE warp per scheduler), so the second set halves its exposed time: group 0 takes accumulator 0 and group 1
+    // accumulator 1 (STORE, NQ), or each group half of the columns of both (COSINE).
+    const int ew = warp & 3;                       // the tensor-memory lane quarter this warp may read
+    const int grp = (warp - 4) >> 2;               // 0: warps 4-7, 1: warps 8-11
     const int row = ew * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16);
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const Item it = decode_item(P, item);
       epi_bar_sync();                              // previous item's readers of s_bias are done
-      for (int i = threadIdx.x - 128; i < BN; i += 128) s_bias[i] = P.bias[it.chunk * BN + i];
+      for (int i = threadIdx.x - 128; i < BN; i += EPI_THREADS) s_bias[i] = P.bias[it.chunk * BN + i];
       epi_bar_sync();
-      const int x = it.x0 + row % P.BW, y = it.y0 + row / P.BW;
+      const int x = it.x0 + (row & (P.BW - 1)), y = it.y0 + (row >> P.bw_shift);
       const bool valid = x < P.W && y < P.H;
       const size_t pix = (size_t)y * P.W + x;
       mbar_wait(tmem_full, tphase);
@@ -288,14 +298,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (EPI == EPI_STORE_RELU || EPI == EPI_STORE) {
         const int n_acc = it.single ? 1 : 2;
 #pragma unroll 1
-        for (int acc = 0; acc < n_acc; ++acc) {
+        for (int acc = grp; acc < n_acc; acc += 2) {
           const int img = acc ? it.img1 : it.img0;
           // 64 output channels (128 B of bf16) per step.  A thread owns a ROW of the accumulator, but rows are Cout*2 bytes
           // apart in the output: storing from the row owner is 32 scattered 16-byte writes per instruction (ncu: the epilogue
           // warps sat on the store queue and the tensor pipe idled 48 % of em_conv1).  So each warp transposes its 32 rows x
           // 128 B through a 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row: conflict-free both ways) and stores
           // with 8 lanes per row: four full 128-byte lines per instruction.
-          uint4* tile = reinterpret_cast<uint4*>(s_w2t) + ew * 256;          // [32 rows][8 chunks of 16 B]
+          uint4* tile = reinterpret_cast<uint4*>(s_w2t) + (warp - 4) * 256;  // [32 rows][8 chunks of 16 B]
+          // the 8 rows this lane stores (4k + lane/8) and its 16-byte chunk are the same for every column step of the item:
+          // their element offsets are computed once (BW is a power of two: shifts, no divisions in the store loop)
+          const int ch = lane & 7;
+          int roff[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr = ew * 32 + 4 * k + (lane >> 3);
+            const int xx = it.x0 + (rr & (P.BW - 1)), yy = it.y0 + (rr >> P.bw_shift);
+            roff[k] = (xx < P.W && yy < P.H) ? (yy * P.W + xx) * P.Cout + ch * 8 : -1;
+          }
+          __nv_bfloat16* obase = P.out + (size_t)img * P.H * P.W * P.Cout + (size_t)it.chunk * BN;
 #pragma unroll 1
           for (int c0 = 0; c0 < BN; c0 += 64) {
             float v[64];
@@ -319,12 +340,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const int r = 4 * k + (lane >> 3), ch = lane & 7;              // row inside this warp's 32, 16-byte chunk
+              const int r = 4 * k + (lane >> 3);
               const uint4 val = tile[r * 8 + (ch ^ (r & 7))];
-              const int rr = ew * 32 + r;
-              const int xx = it.x0 + rr % P.BW, yy = it.y0 + rr / P.BW;
-              if (xx < P.W && yy < P.H)
-                *reinterpret_cast<uint4*>(P.out + (((size_t)img * P.H + yy) * P.W + xx) * P.Cout + (size_t)it.chunk * BN + c0 + ch * 8) = val;
+              if (roff[k] >= 0) *reinterpret_cast<uint4*>(obase + roff[k] + c0) = val;
             }
             __syncwarp();
           }
@@ -333,19 +351,20 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // acc0 = image b of Concat_0(conv_feat, warp_feat) = current-frame embedding, acc1 = warped one (SYM:133-138)
         float scc = 0.f, sww = 0.f, swc = 0.f;
         float bc[2][32], bw[2][32];
-        tmem_ld32(taddr, bc[0]);
-        tmem_ld32(taddr + BN, bw[0]);
+        const int cbase = grp * (BN / 2);          // this group's half of the columns
+        tmem_ld32(taddr + cbase, bc[0]);
+        tmem_ld32(taddr + BN + cbase, bw[0]);
 #pragma unroll 2
-        for (int i = 0; i < BN / 32; ++i) {
+        for (int i = 0; i < BN / 64; ++i) {
           float* ec = bc[i & 1];
           float* ewp = bw[i & 1];
           tmem_ld_wait_for(ec);
           tmem_ld_wait_for(ewp);
-          if (i + 1 < BN / 32) {
-            tmem_ld32(taddr + (i + 1) * 32, bc[(i + 1) & 1]);
-            tmem_ld32(taddr + BN + (i + 1) * 32, bw[(i + 1) & 1]);
+          if (i + 1 < BN / 64) {
+            tmem_ld32(taddr + cbase + (i + 1) * 32, bc[(i + 1) & 1]);
+            tmem_ld32(taddr + BN + cbase + (i + 1) * 32, bw[(i + 1) & 1]);
           }
-          const int c0 = i * 32;
+          const int c0 = cbase + i * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float b = s_bias[c0 + j];
@@ -357,7 +376,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (valid) {
           const size_t NP = (size_t)(P.NB / 2) * P.H * P.W;
-          float* dst = P.partial + (size_t)it.chunk * 3 * NP + (size_t)it.pair * P.H * P.W + pix;
+          float* dst = P.partial + (size_t)(it.chunk * 2 + grp) * 3 * NP + (size_t)it.pair * P.H * P.W + pix;
           dst[0] = scc;
           dst[NP] = sww;
           dst[2 * NP] = swc;
@@ -365,7 +384,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {   // EPI_NQ
         const int n_acc = it.single ? 1 : 2;
 #pragma unroll 1
-        for (int acc = 0; acc < n_acc; ++acc) {
+        for (int acc = grp; acc < n_acc; acc += 2) {
           float q[NQ_MID];
 #pragma unroll
           for (int j = 0; j < NQ_MID; ++j) q[j] = s_nq[j];                 // Nq_conv2 bias
@@ -511,6 +530,9 @@ const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int
   if (P.taps != 1 && P.taps != 9) return "kernel must be 1x1 or 3x3";
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) return "activation / weight pointers must be 16-byte aligned";
   pick_tile(P.H, P.W, &P.BW, &P.BH);
+  P.bw_shift = 0;
+  while ((1 << P.bw_shift) < P.BW) ++P.bw_shift;
+  if ((long long)P.H * P.W * P.Cout >= (1LL << 31)) return "one image's output must stay below 2^31 elements";
   P.tiles_x = (P.W + P.BW - 1) / P.BW;
   P.tiles_y = (P.H + P.BH - 1) / P.BH;
   P.n_chunks = P.Cout / BN;

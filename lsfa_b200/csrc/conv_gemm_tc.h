@@ -14,11 +14,11 @@ struct ConvParams {
   int NB, H, W, Cin, Cout, taps;        // NB images (even: pairs b, b + NB/2), stride-1 'same' convolution, taps = 1 | 9
   const float* bias;                    // (Cout)
   __nv_bfloat16* out;                   // STORE: (NB,H,W,Cout) bf16
-  float* partial;                       // COSINE: (Cout/256, 3, NB/2 * H*W) f32
+  float* partial;                       // COSINE: (2 * Cout/256, 3, NB/2 * H*W) f32 (two column halves per chunk)
   float* logits;                        // NQ: (NB/2, 2, H, W) f32
   const float *nq_w2, *nq_b2, *nq_w3, *nq_b3;   // NQ tail: (16,256), (16), (16), (1)
   // tiling (filled by launch_conv)
-  int BW, BH, tiles_x, tiles_y, n_chunks, kc_per_tap, k_steps, num_items, pair_items;
+  int BW, BH, bw_shift, tiles_x, tiles_y, n_chunks, kc_per_tap, k_steps, num_items, pair_items;
 };
 
 // nullptr = enqueued; otherwise a static message (nothing was launched)

@@ -74,6 +74,7 @@ struct AggParams {
   unsigned* sched;             // zeroed counter(s) for dynamic work claims, or NULL = static split
   long long pool_base;         // all-TMA kernel: items [0,pool_base) are split statically, the rest claimed from sched[0]
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
+  int canon;                   // the record pre-pass writes canonical_taps() records (all-TMA NCHW kernels)
   int coop;                    // all-TMA NCHW kernel launched cooperatively: its own consumers build the records, then a
                                // grid-wide barrier - the one-launch form for small batches (no pre-pass, no memset)
   int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory
@@ -123,6 +124,7 @@ struct PixelRec {
   float w00, w01, w10, w11;   // bilinear weights (x ww after fold_blend)
   float ww, wc;               // blend weights of the warped source / the current feature
   int i00, i01, i10, i11;     // element offsets inside one key plane
+  int edge;                   // bit 0: x0 < 0, bit 1: x0 > Wk-2, bit 2: y0 < 0, bit 3: y0 > Hk-2 (see canonical_taps)
 };
 
 __device__ __forceinline__ PixelRec make_taps(float gx, float gy, int Hk, int Wk, float wk_m1,
@@ -149,9 +151,31 @@ __device__ __forceinline__ PixelRec make_taps(float gx, float gy, int Hk, int Wk
   t.i01 = ya * Wk + xb;
   t.i10 = yb * Wk + xa;
   t.i11 = yb * Wk + xb;
+  t.edge = (x0 < 0 ? 1 : 0) | (x0 > Wk - 2 ? 2 : 0) | (y0 < 0 ? 4 : 0) | (y0 > Hk - 2 ? 8 : 0);
   t.ww = 1.0f;
   t.wc = 0.0f;
   return t;
+}
+
+// Canonical form of a record for the shared-memory gather of the all-TMA NCHW kernels: the four taps become the 2x2
+// block at ONE base offset (base, base+1, base+Wk, base+Wk+1), all inside the plane (needs Hk, Wk >= 2), so the inner
+// loop needs one offset register per pixel and no unpacking.  At a plane border the block is shifted inwards and the
+// weights move with their taps: the slot a tap leaves gets weight 0 (it already was 0: that tap lay outside the plane)
+// and the non-zero terms keep their relative order in the fma chain of tap_chain(), so with finite key values the result
+// is the same float (a zero-weight term adds exactly nothing).
+__device__ __forceinline__ void canonical_taps(PixelRec& t, int Hk, int Wk) {
+  const int y0 = t.i00 / Wk, x0 = t.i00 - y0 * Wk;        // clamped top-left tap
+  const int bx = min(x0, Wk - 2), by = min(y0, Hk - 2);
+  float a = t.w00, b = t.w01, c = t.w10, d = t.w11;
+  if (t.edge & 1) { a = b; b = 0.0f; c = d; d = 0.0f; }   // left of the plane: the right column becomes the block's left one
+  if (t.edge & 2) { b = a; a = 0.0f; d = c; c = 0.0f; }   // last column: the left column becomes the block's right one
+  if (t.edge & 4) { a = c; b = d; c = 0.0f; d = 0.0f; }   // above the plane
+  if (t.edge & 8) { c = a; d = b; a = 0.0f; b = 0.0f; }   // last row
+  t.w00 = a; t.w01 = b; t.w10 = c; t.w11 = d;
+  t.i00 = by * Wk + bx;
+  t.i01 = t.i00 + 1;
+  t.i10 = t.i00 + Wk;
+  t.i11 = t.i10 + 1;
 }
 
 // Fold the warped source's blend weight into the tap weights: one multiply per pixel instead

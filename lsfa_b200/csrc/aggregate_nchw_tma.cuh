@@ -294,11 +294,13 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   const int warp = tid >> 5;
   const bool has_bypass = P.bypass != nullptr;
 
+  uint64_t* rec_issued = reinterpret_cast<uint64_t*>(smem_raw + 192);   // cooperative form: see the producer's first loads
   if (tid == 0) {
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&done[s], kTmaConsumerWarps);
     }
+    mbar_init(rec_issued, kTmaConsumerWarps);
     fence_barrier_init();
   }
   __syncthreads();
@@ -422,6 +424,10 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       int n, chunk;
       int live = 0;                                    // stages holding a real item
       bool stopped = false;
+      // cooperative form: the handful of loads the record math starts from (a few KB for the whole grid) are the head of the
+      // launch's critical path (loads -> index math -> grid barrier -> first item); issued after this CTA's share of the
+      // ~25 MB stage prefetch they queue behind it and land 1-2 us late, so the prefetch waits until they are out
+      if (P.coop) mbar_wait(rec_issued, 0u);
       for (int s = 0; s < P.stages; ++s) {
         if (next_item(n, chunk)) {
           issue_loads(s, n, chunk);
@@ -464,20 +470,37 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
   if (P.coop) {
     // one-launch form (small batches: the reference's batch-1 mode): the index math of the whole batch - at most a pixel
     // or two per consumer thread of the grid - is done here instead of in a pre-pass kernel, then a grid-wide barrier
+    // pixels are dealt out by warp, round robin over the CTAs of the grid (one frame = 75 warps: one warp in each of 75 SMs
+    // instead of 15 warps in each of 5: the FP64 / division work of the index math does not queue)
     uint4* rec = const_cast<uint4*>(P.records);
     const long long total = (long long)P.N * P.HW;
-    for (long long i = (long long)blockIdx.x * kTmaConsumers + tid; i < total; i += (long long)gridDim.x * kTmaConsumers) {
-      const int n = (int)(i / P.HW);
-      const int p = (int)(i - (long long)n * P.HW);
-      if (has_bypass && __ldg(P.bypass + n) != 0) continue;
+    const long long step = (long long)gridDim.x * kTmaConsumerWarps * 32;
+    bool told = false;
+    for (long long i = ((long long)warp * gridDim.x + blockIdx.x) * 32 + (tid & 31);; i += step) {
+      const bool live = i < total;
+      int n = 0, p = 0;
+      if (live) {
+        n = (int)(i / P.HW);
+        p = (int)(i - (long long)n * P.HW);
+      }
+      const bool work = live && !(has_bypass && __ldg(P.bypass + n) != 0);
       const int y = p / P.W, x = p - y * P.W;
-      const PixelLoads ld = issue_pixel_loads(P, n, y, x);
-      PixelRec t = finish_pixel(P, ld, n, y, x);
-      canonical_taps(t, P.Hk, P.Wk);
-      uint4 a, b;
-      pack_record(t, a, b);
-      __stcg(rec + 2 * i, a);
-      __stcg(rec + 2 * i + 1, b);
+      PixelLoads ld;
+      if (work) ld = issue_pixel_loads(P, n, y, x);
+      if (!told) {                                   // this warp's first loads are out (or it has none)
+        told = true;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(rec_issued);
+      }
+      if (!__any_sync(0xffffffffu, live)) break;
+      if (work) {
+        PixelRec t = finish_pixel(P, ld, n, y, x);
+        canonical_taps(t, P.Hk, P.Wk);
+        uint4 a, b;
+        pack_record(t, a, b);
+        __stcg(rec + 2 * i, a);
+        __stcg(rec + 2 * i + 1, b);
+      }
     }
     __threadfence();
     cooperative_groups::this_grid().sync();

@@ -15,14 +15,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblsfa_b200.so")
-SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "prep_ops.cu", "coviar_accumulate.cu", "sampler_backward.cu", "cosine_nchw.cu", "conv_gemm_tc.cu", "host_pipeline.cu", "aggregate_backward.cu",
+SOURCES = ["cabi.cu", "aggregate_nchw.cu", "aggregate_nhwc.cu", "aggregate_nhwc_win.cu", "prep_ops.cu", "coviar_accumulate.cu", "sampler_backward.cu", "cosine_nchw.cu", "conv_gemm_tc.cu", "host_pipeline.cu", "aggregate_backward.cu",
            "plane_var0.cu", "plane_var3.cu",
            "tma_var1.cu", "tma_var2.cu", "tma_var3.cu", "tma_var4.cu",
            "tma2_var1.cu", "tma2_var2.cu", "tma2_var3.cu", "tma2_var4.cu"]
 HEADERS = [os.path.join(CSRC, "lsfa_device.cuh"), os.path.join(CSRC, "aggregate_nchw_plane.cuh"),
            os.path.join(CSRC, "plane_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma.cuh"),
            os.path.join(CSRC, "tma_variant_impl.inc"), os.path.join(CSRC, "aggregate_nchw_tma2.cuh"),
-           os.path.join(CSRC, "aggregate_nhwc_tma.cuh"),
+           os.path.join(CSRC, "aggregate_nhwc_tma.cuh"), os.path.join(CSRC, "aggregate_nhwc_win.cuh"),
            os.path.join(CSRC, "tma2_variant_impl.inc"), os.path.join(CSRC, "conv_gemm_tc.h"), os.path.join(CSRC, "aggregate_backward.h"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "lsfa_ops.h")]
 

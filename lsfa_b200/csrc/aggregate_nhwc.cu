@@ -377,8 +377,10 @@ static int nhwc_grid(long long work_groups) {
   return (int)g;
 }
 
-// kernel: 0 = auto (all-TMA where it applies, else the LDG/STG tile kernel), 1 = LDG/STG tile kernel,
-// 3 = all-TMA or cudaErrorNotSupported
+cudaError_t launch_agg_nhwc_win(const AggParams& P_in, bool bf16, int var, cudaStream_t st);   // aggregate_nhwc_win.cu
+
+// kernel: 0 = auto, 1 = LDG/STG tile kernel, 3 = all-TMA gather-by-bulk-copy or cudaErrorNotSupported,
+// 5 = window-resident all-TMA (tensor maps) or cudaErrorNotSupported
 cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaStream_t st) {
   AggParams P = P_in;
   const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kTileH - 1) / kTileH;
@@ -396,6 +398,7 @@ cudaError_t launch_agg_nhwc(const AggParams& P_in, bool bf16, int kernel, cudaSt
     else if (has_scale && has_cur && !has_res) var = kVarScaleCur;
     else if (!has_scale && has_cur && has_res) var = kVarResCur;
   }
+  if (kernel == 5) return launch_agg_nhwc_win(P, bf16, var, st);
   NtPlan Q;
   const char* env = knob("LSFA_NHWC_TMA");                    // ablation knob: LSFA_NHWC_TMA=0 keeps the LDG/STG kernel
   bool want_tma = kernel == 3 || (kernel == 0 && !(env && env[0] == '0'));

@@ -267,10 +267,11 @@ int run_aggregate(const LsfaAggArgs* a, void* stream) {
       return cuda_result(lsfa::launch_agg_nchw_plane(P, smem, st), "agg_nchw_plane launch");
     return cuda_result(lsfa::launch_agg_nchw_generic(P, st), "agg_nchw_generic launch");
   }
-  // channels-last: force_generic 0 = auto (all-TMA kernel where it applies), 1 = LDG/STG tile kernel, 3 = all-TMA or fail.
-  // An optional 64-byte workspace holds the claim counter of the all-TMA kernel (NULL = static batch stride).
-  if (a->force_generic != 0 && a->force_generic != 1 && a->force_generic != 3)
-    return fail(LSFA_E_BADARG, "force_generic %d is not defined for the channels-last layouts (0, 1 or 3)", a->force_generic);
+  // channels-last: force_generic 0 = auto, 1 = LDG/STG tile kernel, 3 = all-TMA gather-by-bulk-copy or fail,
+  // 5 = window-resident all-TMA (tensor maps) or fail.
+  // An optional 64-byte workspace holds the claim counter of the all-TMA kernels (NULL = static stride).
+  if (a->force_generic != 0 && a->force_generic != 1 && a->force_generic != 3 && a->force_generic != 5)
+    return fail(LSFA_E_BADARG, "force_generic %d is not defined for the channels-last layouts (0, 1, 3 or 5)", a->force_generic);
   if (a->workspace && a->workspace_bytes >= kNhwcWorkspaceBytes && (reinterpret_cast<uintptr_t>(a->workspace) % 4) == 0)
     P.sched = static_cast<unsigned*>(a->workspace);
   cudaError_t e = lsfa::launch_agg_nhwc(P, a->layout == LSFA_LAYOUT_NHWC_BF16, a->force_generic, st);

@@ -448,6 +448,66 @@ def test_nhwc_all_tma_kernel_every_variant(ops, cuda, variant, layout, shape):
     assert np.array_equal(got.view(np.uint32), static.view(np.uint32)), "claimed and static batch orders differ"
 
 
+@pytest.mark.parametrize("variant", ["warp", "scale", "scale_cur", "mean", "res_cur"])
+@pytest.mark.parametrize("layout", ["nhwc_f32", "nhwc_bf16"])
+@pytest.mark.parametrize("shape", [(5, 128, 38, 63), (2, 1024, 38, 63), (3, 128, 17, 23), (2, 256, 9, 7), (1, 128, 1, 5), (2, 128, 68, 120)])
+def test_nhwc_window_kernel_every_variant(ops, cuda, variant, layout, shape):
+    """force_generic=5 pins the window-resident channels-last kernel (one tensor-map copy of a 12x12 key window per 8x8
+    output tile and 256-byte channel chunk, zero padding by the copy engine's out-of-bounds fill).  It must agree with the
+    oracle and BIT FOR BIT with the LDG/STG tile kernel, with the claim counter and with the static tile stride.  Shapes
+    cover planes smaller than a tile, tiles overhanging the plane on both sides, bypass frames, ragged raw MV images."""
+    N, C, H, W = shape
+    bf16 = layout == "nhwc_bf16"
+    d = make_case(21 + N + C, N, C, H, W, with_res=(variant == "res_cur"), raw="ragged" if H > 1 else True,
+                  with_bypass=(variant in ("scale_cur", "mean", "res_cur") and N >= 3))
+    if bf16:
+        for k in ("key", "cur", "scale_map"):
+            d[k] = O.bf16_round(d[k])
+    call = {"warp": ("none", O.W_NONE, dict(use_scale=False)), "scale": ("none", O.W_NONE, {}),
+            "scale_cur": ("logits", O.W_LOGITS, {}), "mean": ("mean", O.W_MEAN, {}),
+            "res_cur": ("add", O.W_ADD, dict(use_scale=False, use_res=True))}[variant]
+    want = oracle_fused(d, call[1], **call[2])
+    got = host(run_fused(ops, cuda, d, call[0], layout, force_generic=5, **call[2]))
+    if bf16:
+        assert_close_bf16(got, want, what="nhwc window %s %s" % (variant, shape))
+    else:
+        assert_close_f32(got, want, scale=max(np.abs(d["key"]).max(), np.abs(d["cur"]).max()), what="nhwc window %s %s" % (variant, shape))
+    ldg = host(run_fused(ops, cuda, d, call[0], layout, force_generic=1, **call[2]))
+    assert np.array_equal(got.view(np.uint32), ldg.view(np.uint32)), "window and LDG/STG kernels differ"
+    static = host(run_fused(ops, cuda, d, call[0], layout, force_generic=5, workspace=False, **call[2]))
+    assert np.array_equal(got.view(np.uint32), static.view(np.uint32)), "claimed and static tile orders differ"
+
+
+@pytest.mark.parametrize("max_px", [96, 400, 4000])
+def test_nhwc_window_kernel_large_motion_falls_back_to_per_pixel_boxes(ops, cuda, max_px):
+    """Motion larger than the window slack (taps of one 8x8 tile spread over more than 12 key pixels, or leaving the plane
+    altogether): the tile is served as gather items, each pixel with its own 2x2 box - same bits as the tile kernel - and
+    the shared-key (tile_as) form on top."""
+    d = make_case(500 + max_px, 4, 256, 38, 63, max_px=max_px, with_bypass=True, shared_key=True)
+    for layout in ("nhwc_bf16", "nhwc_f32"):
+        dd = dict(d)
+        if layout == "nhwc_bf16":
+            for k in ("key", "cur", "scale_map"):
+                dd[k] = O.bf16_round(d[k])
+        got = host(run_fused(ops, cuda, dd, "logits", layout, force_generic=5))
+        ldg = host(run_fused(ops, cuda, dd, "logits", layout, force_generic=1))
+        assert np.array_equal(got.view(np.uint32), ldg.view(np.uint32)), (layout, max_px)
+
+
+def test_nhwc_window_kernel_key_plane_of_another_size(ops, cuda):
+    """BilinearSampler with a data plane that is not the output's size (Hi x Wi != Ho x Wo) through the window kernel."""
+    rng = np.random.default_rng(5)
+    N, C, Hk, Wk, H, W = 2, 128, 21, 40, 13, 18
+    key = O.synth_features(rng, (N, C, Hk, Wk))
+    grid = rng.uniform(-1.2, 1.2, size=(N, 2, H, W)).astype(np.float32)
+    want = O.bilinear_sampler(key, grid)
+    kt = ops.to_nhwc(dev(key, cuda), torch.float32)
+    outs = [host(ops.to_nchw(ops.warp_scale_aggregate(kt, dev(grid, cuda), flow_kind="grid", layout="nhwc_f32", force_generic=fg)))
+            for fg in (5, 1)]
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert_close_f32(outs[0], want, scale=np.abs(key).max(), what="window kernel, other plane size")
+
+
 def test_nhwc_all_tma_kernel_full_size_and_shared_key(ops, cuda):
     """Config-3 shape (1024 x 38 x 63 bf16, raw int32 MVs) with more batches than one wave of CTAs, and the tile_as
     form (one key feature shared by every frame through key_index)."""

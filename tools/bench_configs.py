@@ -180,9 +180,10 @@ def nhwc_rows(dev, pk, quick, only_tma=False):
     C, H, W = 1024, 38, 63
     HW = H * W
     F4, F2 = C * HW * 4, C * HW * 2
-    kinds = ((0, None, ""), (0, False, ", static batch stride"), (1, None, ", LDG/STG tile kernel"))
+    kinds = ((0, None, ""), (0, False, ", static batch stride"), (1, None, ", LDG/STG tile kernel"),
+             (3, None, ", gather-by-bulk-copy kernel"), (5, None, ", window-resident kernel"))
     if only_tma:
-        kinds = (kinds[0], kinds[0], kinds[0])
+        kinds = (kinds[0], kinds[3], kinds[3], kinds[3], kinds[4])
     N = 64
     d = synth(N, C, H, W, 600, 1000, dev)
     Nb = 128 if quick else 512
@@ -195,7 +196,7 @@ def nhwc_rows(dev, pk, quick, only_tma=False):
         p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
                                   weight_mode="logits", logits=lgb, layout="nhwc_bf16", force_generic=fg, workspace=ws)
         row("cfg3 V2 bf16 NHWC batch %d%s" % (Nb, nm), Nb, 4 * F2 + 40 * HW, time_ms(lambda: p.run(s), 3, 10), pk, "ablation" if nm else "")
-    for fg, ws, nm in (kinds[0], kinds[2]):
+    for fg, ws, nm in (kinds[0], kinds[2], kinds[3], kinds[4]):
         p = ops.PreparedAggregate(nh["key"], mvb, flow_kind="raw", cur=nh["cur"], res=resb, rnet_w=d["rnet_w"], rnet_b=d["rnet_b"],
                                   weight_mode="add", layout="nhwc_bf16", force_generic=fg, workspace=ws)
         row("V1 shipped non-key path bf16 NHWC batch %d%s" % (Nb, nm), Nb, 3 * F2 + 44 * HW + 16384, time_ms(lambda: p.run(s), 3, 10), pk,
@@ -233,7 +234,7 @@ def nhwc_rows(dev, pk, quick, only_tma=False):
     N4 = 32 if quick else 128
     d4 = synth(N4, C, H4, W4, 1080, 1920, dev, max_px=96)
     nh = {k: ops.to_nhwc(d4[k], torch.bfloat16) for k in ("key", "cur", "scale_map")}
-    for fg, ws, nm in (kinds[0], kinds[2]):
+    for fg, ws, nm in (kinds[0], kinds[2], kinds[3], kinds[4]):
         p = ops.PreparedAggregate(nh["key"], d4["mv"], flow_kind="raw", cur=nh["cur"], scale_map=nh["scale_map"],
                                   weight_mode="logits", logits=d4["logits"], layout="nhwc_bf16", force_generic=fg, workspace=ws)
         row("cfg4 V2 bf16 NHWC 68x120 batch %d%s" % (N4, nm), N4, 4 * C * H4 * W4 * 2 + 40 * H4 * W4, time_ms(lambda: p.run(s), 3, 10), pk,

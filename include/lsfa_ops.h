@@ -135,7 +135,9 @@ typedef struct LsfaAggArgs {
                                 3 all-TMA warp-specialised, 4 its experimental 2-CTA-cluster form with a multicast
                                 key load (never chosen automatically); 3 and 4 fail if the kernel cannot serve the args.
                                 Channels-last layouts: 0 auto (all-TMA gather-by-bulk-copy kernel where it applies),
-                                1 LDG/STG tile kernel, 3 all-TMA or LSFA_E_UNSUPPORTED */
+                                1 LDG/STG tile kernel, 3 all-TMA gather-by-bulk-copy or LSFA_E_UNSUPPORTED,
+                                5 window-resident all-TMA kernel on tensor maps (C * element size a multiple of 256 bytes)
+                                or LSFA_E_UNSUPPORTED (never chosen automatically) */
 } LsfaAggArgs;
 
 LSFA_API int         lsfa_version(void);

@@ -233,9 +233,10 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
               v01[g] = *reinterpret_cast<const float*>(top + 4);
               v10[g] = *reinterpret_cast<const float*>(bot);
               v11[g] = *reinterpret_cast<const float*>(bot + 4);
-              // slots past the plane read the stage's tail padding (allocated, see plan_tma_kernel) and are not written
-              sc[g] = has_scale ? sc_s[j * kTmaConsumers] : 1.0f;
-              cu[g] = has_cur ? io_s[j * kTmaConsumers] : 0.0f;
+              const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written (a read there would
+                                                   // land in the next plane, which its owner rewrites in place)
+              sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
+              cu[g] = (has_cur && ok) ? io_s[j * kTmaConsumers] : 0.0f;
             }
           }
 #pragma unroll

@@ -456,7 +456,8 @@ def warp_scale_aggregate(key, flow, **kw) -> torch.Tensor:
     'logits'|'cosine'), logits (N,2,H,W), emb_warp, emb_cur, bypass (N,) uint8, key_index (N,)
     int32, flow_kind ('flow'|'grid'|'raw'|'coviar'), im_scale, pool_mode, negate, flipped, layout ('nchw'|'nhwc_f32'|
     'nhwc_bf16'), out, req, workspace, force_generic (kernel choice - NCHW: 0 auto, 1 generic gather, 2 plane-resident
-    LDG/STG, 3 all-TMA, 4 2-CTA cluster form; channels-last: 0 auto, 1 LDG/STG tile kernel, 3 all-TMA).
+    LDG/STG, 3 all-TMA, 4 2-CTA cluster form; channels-last: 0 auto, 1 LDG/STG tile kernel, 3 all-TMA gather by bulk copy,
+    5 window-resident all-TMA on tensor maps).
     ``workspace``: None = allocated here when the chosen path can use one, False = none (static work split).
     """
     args, out, _keep = _build_args(key, flow, **kw)

@@ -21,6 +21,10 @@ bench)
 tables)
   timeout 1200 python tools/bench_configs.py > gpurun_out/configs_table_$TAG.jsonl 2> gpurun_out/configs_table_$TAG.err; echo "configs rc=$?"
   timeout 600 python tools/bench_streams.py --streams 64 256 1024 > gpurun_out/streams_sweep_$TAG.jsonl 2>&1; echo "streams rc=$?"
+  timeout 600 python tools/bench_configs.py --only-motion > gpurun_out/motion_distributions_$TAG.jsonl 2>&1; echo "motion rc=$?"
+  timeout 600 python tools/bench_configs.py --only-keyframe > gpurun_out/keyframe_graphs_$TAG.jsonl 2>&1; echo "keyframe rc=$?"
+  timeout 600 python tools/bench_configs.py --only-nhwc-win > gpurun_out/nhwc_window_$TAG.jsonl 2>&1; echo "window rc=$?"
+  timeout 600 python tools/bench_configs.py --only-single > gpurun_out/single_frame_$TAG.jsonl 2>&1; echo "single rc=$?"
   cut -c1-200 gpurun_out/configs_table_$TAG.jsonl ;;
 profile)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
@@ -29,10 +33,28 @@ profile)
       python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 1 > /dev/null 2>&1; echo "ncu headline rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_tc -s 4 -c 4 -f -o gpurun_out/prof_tc_$TAG \
       python tools/run_keyframe_tc.py 2 > /dev/null 2>&1; echo "ncu tensor-core rc=$?"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mvacc_trace -s 1 -c 1 -f -o gpurun_out/prof_trace_$TAG \
-      python tools/bench_configs.py --only-upstream > /dev/null 2>&1; echo "ncu back-trace rc=$?" ;;
+  timeout 600 ncu --set full --clock-control none -k regex:mvacc_trace -s 1 -c 1 -f -o gpurun_out/prof_trace_$TAG \
+      python tools/bench_configs.py --only-upstream > /dev/null 2>&1; echo "ncu back-trace rc=$?"
+  # the variants that are not HBM bound (motion rows: V0, V1, V2 fp32 NCHW then V0, V1 bf16 NHWC, 23 launches each)
+  timeout 600 ncu --set full --clock-control none -k regex:agg_nchw_tma_kernel -s 10 -c 1 -f -o gpurun_out/prof_v0_nchw_$TAG \
+      python tools/bench_configs.py --only-motion > /dev/null 2>&1; echo "ncu V0 fp32 NCHW rc=$?"
+  timeout 600 ncu --set full --clock-control none -k regex:agg_nhwc_tma_kernel -s 10 -c 1 -f -o gpurun_out/prof_v0_nhwc_$TAG \
+      python tools/bench_configs.py --only-motion > /dev/null 2>&1; echo "ncu V0 bf16 NHWC rc=$?"
+  timeout 600 ncu --set full --clock-control none -k regex:agg_nhwc_tma_kernel -s 33 -c 1 -f -o gpurun_out/prof_v1_nhwc_$TAG \
+      python tools/bench_configs.py --only-motion > /dev/null 2>&1; echo "ncu V1 bf16 NHWC rc=$?"
+  timeout 600 ncu --set full --clock-control none -k regex:agg_nchw_tma_kernel -s 20 -c 1 -f -o gpurun_out/prof_cfg5_$TAG \
+      python tools/bench_streams.py --streams 64 > /dev/null 2>&1; echo "ncu cfg5 rc=$?"
+  timeout 600 ncu --set full --clock-control none -k regex:agg_nhwc_win_kernel -s 5 -c 1 -f -o gpurun_out/prof_win_v0_$TAG \
+      python tools/bench_configs.py --only-nhwc-win > /dev/null 2>&1; echo "ncu window kernel rc=$?"
+  # text summaries for profiles/; gpurun brings back at most 64 MiB, so only the two main reports travel as .ncu-rep
+  for r in tma:64 tc:16 trace:64 v0_nchw:64 v0_nhwc:64 v1_nhwc:64 cfg5:80 win_v0:64; do
+    python tools/ncu_summary.py gpurun_out/prof_${r%%:*}_$TAG.ncu-rep gpurun_out/ncu_${r%%:*}_$TAG.txt ${r##*:} > /dev/null 2>&1
+  done
+  rm -f gpurun_out/prof_trace_$TAG.ncu-rep gpurun_out/prof_v0_nchw_$TAG.ncu-rep gpurun_out/prof_v0_nhwc_$TAG.ncu-rep \
+        gpurun_out/prof_v1_nhwc_$TAG.ncu-rep gpurun_out/prof_cfg5_$TAG.ncu-rep gpurun_out/prof_win_v0_$TAG.ncu-rep
+  ls -la gpurun_out | tail -30 ;;
 sanitize)
-  SEL='all_tma_kernel_every_variant or cooperative or host_aggregator or test_bilinear_sampler or cur_frame_path or fused_golden'
+  SEL='all_tma_kernel_every_variant or window_kernel or cooperative or host_aggregator or test_bilinear_sampler or cur_frame_path or fused_golden'
   for tool in memcheck synccheck racecheck; do
     timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_tc_convs.py tests/test_host_path.py -m gpu -x -q -k "$SEL or conv_bf16 or host_path_matches" > gpurun_out/sanitizer_${TAG}_$tool.log 2>&1
     echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/sanitizer_${TAG}_$tool.log | tail -3

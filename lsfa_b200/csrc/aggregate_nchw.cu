@@ -253,7 +253,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
   const int var = variant_of(P);
   if (var == kVarRuntime) return false;
   if (P.HWk > 16383) return false;                               // tap byte offsets are packed in 16 bits
-  if (P.Hk < 2 || P.Wk < 2) return false;                        // canonical_taps(): a 2x2 block inside the plane
+  if (var == kVarWarpOnly && (P.Hk < 2 || P.Wk < 2)) return false;   // canonical_taps(): a 2x2 block inside the plane
   const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
   for (const void* q : ptrs)
     if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
@@ -314,7 +314,7 @@ bool plan_tma_kernel(AggParams& P, size_t* smem_out) {
 
 cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
-  P.canon = 1;
+  P.canon = variant_of(P) == kVarWarpOnly ? 1 : 0;          // canonical tap records: see tma_consumer_loop
   if (knob("LSFA_TMA_STATIC")) P.sched = nullptr;          // experiment knobs (ablations)
   if (knob("LSFA_TMA_NO_RECORDS")) P.records = nullptr;
   {
@@ -365,7 +365,7 @@ bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
   const size_t kSmemMax = 227 * 1024;
   const int var = variant_of(P);
   if (var == kVarRuntime) return false;
-  if (P.HWk > 16383 || (P.HW % 4) || (P.HWk % 4) || P.Hk < 2 || P.Wk < 2) return false;
+  if (P.HWk > 16383 || (P.HW % 4) || (P.HWk % 4)) return false;
   const void* ptrs[4] = {P.key, P.scale, P.cur, P.out};
   for (const void* q : ptrs)
     if (q && (reinterpret_cast<uintptr_t>(q) % 16)) return false;
@@ -404,7 +404,6 @@ bool plan_tma2_kernel(AggParams& P, size_t* smem_out, bool forced) {
 
 cudaError_t launch_agg_nchw_tma2(const AggParams& Pin, size_t smem, cudaStream_t st) {
   AggParams P = Pin;
-  P.canon = 1;
   long long clusters = sm_count() / 2;
   if (clusters > P.items) clusters = P.items;
   if (P.sched) {

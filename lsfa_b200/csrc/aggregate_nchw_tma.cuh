@@ -57,14 +57,19 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
   const bool has_bypass = P.bypass != nullptr;
   // ================================= consumer warps ==========================================
   float w00[PPT], w01[PPT], w10[PPT], w11[PPT], wc[PPT], ww[PPT];
-  unsigned ob[PPT];                    // byte offset of the 2x2 tap block inside a key plane (canonical_taps)
+  // tap byte offsets inside a key plane: (i00 | i01 << 16), (i10 | i11 << 16).  Warp-only variant (P.canon): the record is
+  // canonical (canonical_taps: the 2x2 block at o_top's low half, rows row_bytes apart), which saves the unpacking -
+  // measured +2.6 % there; the same form costs the HBM-bound headline variant 2.2 % (denser LDS bursts), so it keeps
+  // the packed offsets.
+  unsigned o_top[PPT], o_bot[PPT];
+  constexpr bool canon = DIRECT;       // = the warp-only variant of agg_nchw_tma_kernel; its launcher sets P.canon for the pre-pass
+  const unsigned row_bytes = (unsigned)P.Wk * 4u;
   unsigned valid = 0;
   int cur_vf = -1, n = 0;
   bool byp = false;
   int s = 0;
   unsigned ph = 0;
   const unsigned plane_bytes = (unsigned)P.HWk * 4u;
-  const unsigned row_bytes = (unsigned)P.Wk * 4u;
   const unsigned io_plane_bytes = (unsigned)(P.parts == 1 ? P.HW : P.part_pix) * 4u;
   (void)ww;
   constexpr int JG = PPT > 5 ? 3 : PPT;   // pixel slots handled together (bounds the live registers)
@@ -124,7 +129,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           w00[j] = __uint_as_float(ra[j].x); w01[j] = __uint_as_float(ra[j].y);
           w10[j] = __uint_as_float(ra[j].z); w11[j] = __uint_as_float(ra[j].w);
           wc[j] = __uint_as_float(rb[j].x); ww[j] = __uint_as_float(rb[j].y);
-          ob[j] = rb[j].z & 0xffffu;
+          o_top[j] = rb[j].z; o_bot[j] = rb[j].w;
           if (has_res) {
             const int p = pix0 + tid + j * kTmaConsumers;
             if (p < pend && !byp) {
@@ -146,7 +151,7 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         w00[j] = w01[j] = w10[j] = w11[j] = wc[j] = ww[j] = 0.0f;
-        ob[j] = 0u;                    // slot outside the part: taps read offset 0, store is predicated off
+        o_top[j] = o_bot[j] = 0u;      // slot outside the part: taps read offset 0, store is predicated off
       }
       // phase A0: L2 prefetch of everything the records need, all pixel slots back to back
       if (!byp) {
@@ -177,10 +182,11 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
             valid |= 1u << j;
             if (!byp) {
               PixelRec t = finish_pixel(P, ld[g], n, p / P.W, p % P.W);
-              canonical_taps(t, P.Hk, P.Wk);
+              if (canon) canonical_taps(t, P.Hk, P.Wk);
               w00[j] = t.w00; w01[j] = t.w01; w10[j] = t.w10; w11[j] = t.w11;
               wc[j] = t.wc; ww[j] = t.ww;
-              ob[j] = (unsigned)(t.i00 * 4);
+              o_top[j] = (unsigned)(t.i00 * 4) | ((unsigned)(t.i01 * 4) << 16);
+              o_bot[j] = (unsigned)(t.i10 * 4) | ((unsigned)(t.i11 * 4) << 16);
               if (has_res) {
                 if (RES_REG) {
                   rr0[j % RRN] = __ldg(P.res + ((size_t)n * 3 + 0) * P.HW + p);
@@ -227,12 +233,19 @@ __device__ __forceinline__ void tma_consumer_loop(const AggParams& P, uint64_t* 
           for (int g = 0; g < JG; ++g) {   // all shared-memory reads of the group first ...
             const int j = j0 + g;
             if (j < PPT) {
-              const unsigned char* top = plane_s + ob[j];          // the 2x2 block: two adds, four loads at +0 / +4
-              const unsigned char* bot = top + row_bytes;
-              v00[g] = *reinterpret_cast<const float*>(top);
-              v01[g] = *reinterpret_cast<const float*>(top + 4);
-              v10[g] = *reinterpret_cast<const float*>(bot);
-              v11[g] = *reinterpret_cast<const float*>(bot + 4);
+              if (canon) {
+                const unsigned char* top = plane_s + (o_top[j] & 0xffffu);   // the 2x2 block: two adds, four loads at +0 / +4
+                const unsigned char* bot = top + row_bytes;
+                v00[g] = *reinterpret_cast<const float*>(top);
+                v01[g] = *reinterpret_cast<const float*>(top + 4);
+                v10[g] = *reinterpret_cast<const float*>(bot);
+                v11[g] = *reinterpret_cast<const float*>(bot + 4);
+              } else {
+                v00[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] & 0xffffu));
+                v01[g] = *reinterpret_cast<const float*>(plane_s + (o_top[j] >> 16));
+                v10[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] & 0xffffu));
+                v11[g] = *reinterpret_cast<const float*>(plane_s + (o_bot[j] >> 16));
+              }
               const bool ok = (valid >> j) & 1u;   // slots past the plane are neither read nor written (a read there would
                                                    // land in the next plane, which its owner rewrites in place)
               sc[g] = (has_scale && ok) ? sc_s[j * kTmaConsumers] : 1.0f;
@@ -496,7 +509,7 @@ agg_nchw_tma_kernel(const __grid_constant__ AggParams P) {
       if (!__any_sync(0xffffffffu, live)) break;
       if (work) {
         PixelRec t = finish_pixel(P, ld, n, y, x);
-        canonical_taps(t, P.Hk, P.Wk);
+        if (P.canon) canonical_taps(t, P.Hk, P.Wk);
         uint4 a, b;
         pack_record(t, a, b);
         __stcg(rec + 2 * i, a);

@@ -74,7 +74,7 @@ struct AggParams {
   unsigned* sched;             // zeroed counter(s) for dynamic work claims, or NULL = static split
   long long pool_base;         // all-TMA kernel: items [0,pool_base) are split statically, the rest claimed from sched[0]
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
-  int canon;                   // the record pre-pass writes canonical_taps() records (all-TMA NCHW kernels)
+  int canon;                   // the record pre-pass writes canonical_taps() records (warp-only variant of the all-TMA kernel)
   int coop;                    // all-TMA NCHW kernel launched cooperatively: its own consumers build the records, then a
                                // grid-wide barrier - the one-launch form for small batches (no pre-pass, no memset)
   int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory
@@ -124,7 +124,7 @@ struct PixelRec {
   float w00, w01, w10, w11;   // bilinear weights (x ww after fold_blend)
   float ww, wc;               // blend weights of the warped source / the current feature
   int i00, i01, i10, i11;     // element offsets inside one key plane
-  int edge;                   // bit 0: x0 < 0, bit 1: x0 > Wk-2, bit 2: y0 < 0, bit 3: y0 > Hk-2 (see canonical_taps)
+  int edge;                   // bit 0: x0 < 0, bit 1: x0 > Wk-2, bit 2: y0 < 0, bit 3: y0 > Hk-2 (canonical_taps; window kernel: tap box origin)
 };
 
 __device__ __forceinline__ PixelRec make_taps(float gx, float gy, int Hk, int Wk, float wk_m1,

@@ -41,3 +41,13 @@ def test_tensor_core_unit_contains_tcgen05_and_tma_tensor_sass(lib):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "SYNCS"):
         assert mnemonic in sass, "%s missing from conv_gemm_tc.o" % mnemonic
+
+
+def test_window_kernel_unit_contains_tensor_map_copies(lib):
+    """The window-resident channels-last kernel moves its key windows with tensor-map TMA (UTMALDG), not bulk copies."""
+    obj = os.path.join(ROOT, "lsfa_b200", "lib", "obj", "aggregate_nhwc_win.o")
+    if not os.path.exists(obj):
+        pytest.skip("object file not kept")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass and "SYNCS" in sass
+    assert sass.count("Function :") >= 8          # 2 storage types x 4 compile-time variants

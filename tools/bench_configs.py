@@ -89,6 +89,13 @@ def backward_rows(dev, pk, quick):
             time_ms(lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel=kern), 2, st), pk)
         row("bwd warp: grad_key only (SYM:320-321), fp32 NCHW (%s)" % kern, N, 2 * F4 + 8 * HW,
             time_ms(lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, req_flow="null", workspace=ws, kernel=kern), 2, st), pk)
+    # backward of the fused operator (SYM:306-338): tails (agg_tail_backward_kernel) + the a7/a8 gather on its d/d(warp)
+    lg = d["logits"]
+    for nm, kw, alg in (("V2 (x scale, logits blend): key, flow, scale, cur, logits", dict(cur=d["cur"], scale_map=d["scale_map"], weight_mode="logits", logits=lg), 10 * F4),
+                        ("V1 (+ rnet(res) + cur): key, flow, cur, res, rnet", dict(cur=d["cur"], res=d["res"], rnet_w=d["rnet_w"], rnet_b=d["rnet_b"], weight_mode="add"), 7 * F4)):
+        row("bwd fused " + nm, N, alg,
+            time_ms(lambda: ops.warp_scale_aggregate_backward(og, d["key"], flow, flow_kind="flow", **kw), 2, 5), pk,
+            "bytes: every stream once incl. the d/d(warp) intermediate")
     # smooth motion (every block moves by the same sub-cell vector): short, even lists
     flow2 = torch.full_like(flow, 0.37)
     row("bwd warp: grad_key + grad_flow, uniform flow (gather)", N, 3 * F4 + 16 * HW,

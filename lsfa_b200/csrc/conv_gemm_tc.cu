@@ -430,6 +430,290 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =========================================================================================================
+// 2-CTA form (cta_group::2): a CTA PAIR (thread-block cluster of 2, one TPC) works on one pair item.
+//   CTA r holds the activation tile of image (r ? img1 : img0) and HALF of the weight tile (128 of the 256 filters);
+//   one tcgen05.mma.cta_group::2 (M = 256, N = 256), issued by the leader CTA, multiplies both: each SM reads 4 KB of A
+//   and 4 KB of B per 128 cycles from its own shared memory (64 B/cycle instead of 96) and TMA writes 32 KB per k-step
+//   per SM (instead of 64 KB), so operand traffic fits the 128 B/cycle a shared memory delivers; and each SM's
+//   accumulator is ONE 128 x 256 tile, so two fit in tensor memory: the epilogue of item i overlaps the MMAs of item
+//   i + 1 (the single-CTA kernel above exposes it: em_conv1 spends 10 k of its 27 k cycles per item there).
+//   Barriers: full[s] lives in the leader (its producer arms it for the bytes of BOTH CTAs; the peer's copies signal it
+//   through cp.async.bulk.tensor...cta_group::2), empty[s] / tmem_full[b] are armed in both CTAs by multicast
+//   tcgen05.commit, tmem_empty[b] lives in the leader and collects one arrival per epilogue warp of both CTAs.
+//   Epilogue group g (warps 4-7 | 8-11) drains accumulator buffer g, i.e. every other item.
+// Serves the STORE and NQ epilogues (COSINE needs both images of a pixel in one thread: single-CTA kernel).
+// =========================================================================================================
+constexpr int STAGES2 = 5;
+constexpr int B2_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the weight tile
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;      // 32 KB
+constexpr int EPI2_SMEM_FLOATS = 2 * BN + EPI_TILE_FLOATS + 3 * NQ_MID + 16;
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * STAGE2_BYTES + EPI2_SMEM_FLOATS * 4 + 256;
+static_assert(SMEM2_BYTES <= 227 * 1024, "shared memory budget (2-CTA form)");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// tensor copies whose completion is signalled on a barrier of the LEADER CTA (bar_cluster_addr: shared::cluster address)
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2, const ConvParams P) {
+  static_assert(EPI == EPI_STORE_RELU || EPI == EPI_STORE || EPI == EPI_NQ, "the 2-CTA form serves the STORE and NQ epilogues");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES2 * STAGE2_BYTES);    // [2 groups][BN]
+  float* s_w2t = s_bias + 2 * BN;                                             // STORE: transpose tiles; NQ: [BN][16]
+  float* s_nq = s_w2t + EPI_TILE_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES + EPI2_SMEM_FLOATS * 4);
+  uint64_t* full = bars;                      // [STAGES2] (leader's are used)
+  uint64_t* empty = bars + STAGES2;           // [STAGES2] in each CTA
+  uint64_t* tmem_full = bars + 2 * STAGES2;   // [2] in each CTA
+  uint64_t* tmem_empty = tmem_full + 2;       // [2] (leader's are used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_items = P.num_items;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB2);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * 4);       // one arrival per epilogue warp of the group, both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (EPI == EPI_NQ && warp >= 4) {
+    const int t = threadIdx.x - 128;
+    for (int i = t; i < NQ_MID * BN; i += EPI_THREADS) {
+      const int j = i / BN, c = i % BN;
+      s_w2t[c * NQ_MID + j] = P.nq_w2[i];
+    }
+    if (t < NQ_MID) {
+      s_nq[t] = P.nq_b2[t];
+      s_nq[NQ_MID + t] = P.nq_w3[t];
+    }
+    if (t == 0) s_nq[2 * NQ_MID] = P.nq_b3[0];
+  }
+  __syncthreads();
+  cluster_sync_all();                          // both CTAs' barriers exist before anything remote can arrive on them
+  if (warp == 2) tmem_alloc2(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs: own activation tile + own half of the weight tile) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const Item it = decode_item(P, item);
+        const int img = rank ? it.img1 : it.img0;
+        for (int ks = 0; ks < P.k_steps; ++ks) {
+          const int tap = ks / P.kc_per_tap, kc = ks - tap * P.kc_per_tap;
+          const int dy = P.taps == 9 ? tap / 3 - 1 : 0, dx = P.taps == 9 ? tap % 3 - 1 : 0;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE2_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE2_BYTES);
+          const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
+          tma2_load_4d(st, &tmA, kc * BK, it.x0 + dx, it.y0 + dy, img, fb);
+          tma2_load_2d(st + A_BYTES, &tmB2, tap * P.Cin + kc * BK, it.chunk * BN + (int)rank * (BN / 2), fb);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      uint32_t stage = 0, phase = 0;
+      int n = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++n) {
+        const int b = n & 1;
+        mbar_wait(&tmem_empty[b], (((unsigned)n >> 1) & 1u) ^ 1u);   // both CTAs' epilogues have drained this buffer
+        tcgen05_fence_after();
+        for (int ks = 0; ks < P.k_steps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint64_t da = make_kmajor_sw128_desc(a0);
+          const uint64_t db = make_kmajor_sw128_desc(a0 + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma2_bf16(tmem_base + b * BN, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+          umma2_commit_both(&empty[stage]);
+          if (ks == P.k_steps - 1) umma2_commit_both(&tmem_full[b]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: group g drains accumulator buffer g (every other item) =====================
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;
+    const int row = ew * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)grp * BN;
+    float* bias_g = s_bias + grp * BN;
+    const uint32_t te_addr = mapa_shared(smem_u32(&tmem_empty[grp]), 0);
+    unsigned use = 0;                            // uses of this group's buffer so far
+    int n = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++n) {
+      if ((n & 1) != grp) continue;
+      const Item it = decode_item(P, item);
+      const int img = rank ? it.img1 : it.img0;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // previous item's readers of bias_g are done
+      for (int i = (threadIdx.x - 128) & 127; i < BN; i += 128) bias_g[i] = P.bias[it.chunk * BN + i];
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      const int x = it.x0 + (row & (P.BW - 1)), y = it.y0 + (row >> P.bw_shift);
+      const bool valid = x < P.W && y < P.H;
+      const size_t pix = (size_t)y * P.W + x;
+      mbar_wait(&tmem_full[grp], use & 1u);
+      tcgen05_fence_after();
+      if (EPI == EPI_STORE_RELU || EPI == EPI_STORE) {
+        uint4* tile = reinterpret_cast<uint4*>(s_w2t) + (warp - 4) * 256;
+        const int ch = lane & 7;
+        int roff[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = ew * 32 + 4 * k + (lane >> 3);
+          const int xx = it.x0 + (rr & (P.BW - 1)), yy = it.y0 + (rr >> P.bw_shift);
+          roff[k] = (xx < P.W && yy < P.H) ? (yy * P.W + xx) * P.Cout + ch * 8 : -1;
+        }
+        __nv_bfloat16* obase = P.out + (size_t)img * P.H * P.W * P.Cout + (size_t)it.chunk * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          float v[64];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld32(taddr + c0 + 32, v + 32);
+          tmem_ld_wait_for(v);
+          tmem_ld_wait_for(v + 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = q * 8 + 2 * j;
+              float a = v[c] + bias_g[c0 + c], b = v[c + 1] + bias_g[c0 + c + 1];
+              if (EPI == EPI_STORE_RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            tile[lane * 8 + (q ^ (lane & 7))] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = 4 * k + (lane >> 3);
+            const uint4 val = tile[r * 8 + (ch ^ (r & 7))];
+            if (roff[k] >= 0) *reinterpret_cast<uint4*>(obase + roff[k] + c0) = val;
+          }
+          __syncwarp();
+        }
+      } else {   // EPI_NQ
+        float q[NQ_MID];
+#pragma unroll
+        for (int j = 0; j < NQ_MID; ++j) q[j] = s_nq[j];
+        float buf[2][32];
+        tmem_ld32(taddr, buf[0]);
+#pragma unroll 2
+        for (int i = 0; i < BN / 32; ++i) {
+          float* v = buf[i & 1];
+          tmem_ld_wait_for(v);
+          if (i + 1 < BN / 32) tmem_ld32(taddr + (i + 1) * 32, buf[(i + 1) & 1]);
+          const int c0 = i * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float a = fmaxf(v[c] + bias_g[c0 + c], 0.f);
+            const float4* wr = reinterpret_cast<const float4*>(s_w2t + (c0 + c) * NQ_MID);
+#pragma unroll
+            for (int j4 = 0; j4 < NQ_MID / 4; ++j4) {
+              const float4 w = wr[j4];
+              q[4 * j4 + 0] = fmaf(w.x, a, q[4 * j4 + 0]);
+              q[4 * j4 + 1] = fmaf(w.y, a, q[4 * j4 + 1]);
+              q[4 * j4 + 2] = fmaf(w.z, a, q[4 * j4 + 2]);
+              q[4 * j4 + 3] = fmaf(w.w, a, q[4 * j4 + 3]);
+            }
+          }
+        }
+        float o = s_nq[2 * NQ_MID];
+#pragma unroll
+        for (int j = 0; j < NQ_MID; ++j) o = fmaf(s_nq[NQ_MID + j], fmaxf(q[j], 0.f), o);
+        if (valid) P.logits[((size_t)it.pair * 2 + rank) * P.H * P.W + pix] = o;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te_addr);
+      ++use;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // the peer's tensor memory reads and remote arrivals are done
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc2(tmem_base, TMEM_COLS);
+  }
+}
+
 // cosine logits from the per-chunk partial sums (fixed summation order: deterministic).  compute_weight SYM:111-116 with
 // MXNet's L2Normalization(mode='channel'): e / sqrt(sum e^2 + 1e-10);  logits[n,0] = <e_warp^, e_cur^>, [n,1] = <e_cur^, e_cur^>
 __global__ void cosine_from_partials_kernel(const float* __restrict__ partial, float* __restrict__ logits, int n_chunks, int N,
@@ -509,6 +793,41 @@ static const char* make_maps(const void* x, const void* w, const ConvParams& P, 
   return nullptr;
 }
 
+// 2-CTA form: grid = 2 x (clusters that can be co-resident), cluster dims are a compile-time attribute of the kernel
+template <int EPI>
+static const char* launch_epi2(const CUtensorMap& tmA, const CUtensorMap& tmB2, const ConvParams& P, cudaStream_t stream, bool* launched) {
+  static int max_clusters = -1;    // benign race: idempotent
+  auto kfn = conv_gemm_tc2_kernel<EPI>;
+  if (max_clusters < 0) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      max_clusters = 0;
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * 74);
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = SMEM2_BYTES;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      max_clusters = n;
+    }
+  }
+  *launched = false;
+  if (max_clusters < 8) return nullptr;          // not worth it / not possible: the caller uses the single-CTA kernel
+  const int clusters = P.num_items < max_clusters ? P.num_items : max_clusters;
+  kfn<<<2 * clusters, NUM_THREADS, SMEM2_BYTES, stream>>>(tmA, tmB2, P);
+  if (cudaPeekAtLastError() != cudaSuccess) {    // e.g. a partition that cannot co-schedule CTA pairs: single-CTA kernel instead
+    cudaGetLastError();
+    max_clusters = 0;
+    return nullptr;
+  }
+  *launched = true;
+  return nullptr;
+}
+
 template <int EPI>
 static const char* launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& P, int sms, cudaStream_t stream) {
   static bool attr_set = false;    // benign race: the attribute is idempotent
@@ -552,6 +871,28 @@ const char* launch_conv(const void* x, const void* w, ConvParams P, int epi, int
   }
   CUtensorMap tmA, tmB;
   if (const char* e = make_maps(x, w, P, &tmA, &tmB)) return e;
+  // CTA-pair form (cta_group::2) for the STORE / NQ epilogues on even image counts: every pair item on a cluster
+  if (epi != EPI_COSINE && !(P.NB & 1) && !(epi == EPI_NQ && P.Cout != BN) && knob("LSFA_TC_NO_PAIR") == nullptr) {
+    ConvParams P2 = P;
+    P2.pair_items = (P.NB / 2) * P.tiles_x * P.tiles_y * P.n_chunks;
+    P2.num_items = P2.pair_items;
+    CUtensorMap tmB2;
+    auto enc = encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)P.taps * P.Cin, (cuuint64_t)P.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)P.taps * P.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2)};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      bool launched = false;
+      const char* e = nullptr;
+      if (epi == EPI_STORE_RELU) e = launch_epi2<EPI_STORE_RELU>(tmA, tmB2, P2, stream, &launched);
+      else if (epi == EPI_STORE) e = launch_epi2<EPI_STORE>(tmA, tmB2, P2, stream, &launched);
+      else e = launch_epi2<EPI_NQ>(tmA, tmB2, P2, stream, &launched);
+      if (e) return e;
+      if (launched) return nullptr;
+    }
+  }
   switch (epi) {
     case EPI_STORE_RELU: return launch_epi<EPI_STORE_RELU>(tmA, tmB, P, sms, stream);
     case EPI_STORE: return launch_epi<EPI_STORE>(tmA, tmB, P, sms, stream);

@@ -41,6 +41,9 @@ def test_tensor_core_unit_contains_tcgen05_and_tma_tensor_sass(lib):
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "SYNCS"):
         assert mnemonic in sass, "%s missing from conv_gemm_tc.o" % mnemonic
+    # the CTA-pair form: tcgen05.mma.cta_group::2, multicast tcgen05.commit, cta_group::2 tensor copies
+    for mnemonic in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMALDG.4D.2CTA"):
+        assert mnemonic in sass, "%s missing from conv_gemm_tc.o" % mnemonic
 
 
 def test_window_kernel_unit_contains_tensor_map_copies(lib):

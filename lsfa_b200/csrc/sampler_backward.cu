@@ -11,7 +11,7 @@
 //   pre-pass (bwd_lists_kernel, once per frame, channel independent): invert the sampling map - for
 //     every INPUT pixel q the list of (output pixel p, tap weight) that touch it, sorted by (p, tap)
 //     (= the order MXNet's sequential CPU loop adds them), stored slot-major (ELL, L slots, 6 B per
-//     entry); entries beyond L go to an overflow list (served by a small atomic fix-up kernel);
+//     entry); entries beyond L go, in order, to an overflow list (served by a small ordered fix-up kernel);
 //     plus a 16-byte record per OUTPUT pixel for the grid gradient (top-left weights, 4 tap offsets).
 //   main kernel (same all-TMA warp-specialised pipeline as agg_nchw_tma_kernel): per (frame, K
 //     channels) the producer lane TMA-loads the data planes and the out_grad planes into a stage;
@@ -20,7 +20,8 @@
 //     list against the out_grad planes in smem, writing grad_data IN PLACE over the data planes;
 //     the producer TMA-stores them (cp.reduce.async.bulk ... add.f32 for req = kAddTo).
 //   HBM: out_grad once, data once (only when d/d(grid) is wanted), grad_data once: 3F (or 2F).
-//   grad_data is deterministic (fixed summation order) unless a list overflowed.
+//   grad_data is deterministic (fixed summation order) for any sampling map: lists longer than L are rebuilt / split in
+//   (p, tap) order by the pre-pass and their tails are added by one thread per channel (bwd_overflow_kernel).
 #include <cstdlib>
 #include <cstring>
 
@@ -46,9 +47,12 @@ struct BwdParams {
   float* ell_w;              // [N][L][HWk]
   unsigned char* ell_cnt;    // [N][HWk]     min(count, L)
   uint4* rec;                // [N][HW]      {wx, wy, off00|off01<<16, off10|off11<<16}, bit 0 of an offset = tap inside
-  unsigned* ovf_count;
-  uint4* ovf;                // {n, q, p, weight bits}
+  unsigned* ovf_count;       // [0] entries, [1] groups
+  uint4* ovf;                // {n, q, p, weight bits}: the entries of one input pixel are contiguous and in (p, tap) order
   unsigned ovf_cap;
+  uint4* ovf_groups;         // {n, q, first entry, entries}: one per input pixel whose list is longer than L
+  unsigned ovf_gcap;
+  int LP;                    // lists pre-pass: slots per input pixel in shared memory (>= L): what is sorted without a rescan
   unsigned* sched;
   long long pool_base;       // items [0,pool_base) split statically, the rest claimed from sched[0]
 };
@@ -139,8 +143,8 @@ constexpr int kBwdListThreads = 512;
 __global__ void __launch_bounds__(kBwdListThreads) bwd_lists_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ __align__(16) unsigned char lsm[];
   int* cnt = reinterpret_cast<int*>(lsm);                                   // [HWk]
-  float* w_s = reinterpret_cast<float*>(lsm + (size_t)((P.HWk + 3) / 4 * 4) * 4);   // [L][HWk]
-  unsigned short* o_s = reinterpret_cast<unsigned short*>(w_s + (size_t)P.L * P.HWk);   // [L][HWk]
+  float* w_s = reinterpret_cast<float*>(lsm + (size_t)((P.HWk + 3) / 4 * 4) * 4);   // [LP][HWk]
+  unsigned short* o_s = reinterpret_cast<unsigned short*>(w_s + (size_t)P.LP * P.HWk);   // [LP][HWk]
   const int n = blockIdx.x, tid = threadIdx.x;
   const bool lists = P.gdata != nullptr;
   if (lists)
@@ -157,24 +161,78 @@ __global__ void __launch_bounds__(kBwdListThreads) bwd_lists_kernel(const __grid
     if (lists) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (!t.ok[k] || t.w[k] == 0.0f) continue;      // a zero weight adds nothing
+        if (!t.ok[k] || t.w[k] == 0.0f) continue;        // a zero weight adds nothing
         const int slot = atomicAdd(&cnt[t.q[k]], 1);
-        if (slot < P.L) {
+        if (slot < P.LP) {                               // LP >= L slots here; lists beyond LP are rebuilt in order below
           w_s[(size_t)slot * P.HWk + t.q[k]] = t.w[k];
           o_s[(size_t)slot * P.HWk + t.q[k]] = (unsigned short)(((unsigned)p << 2) | (unsigned)k);
-        } else {
-          const unsigned i = atomicAdd(P.ovf_count, 1u);
-          if (i < P.ovf_cap) P.ovf[i] = make_uint4((unsigned)n, (unsigned)t.q[k], (unsigned)p, __float_as_uint(t.w[k]));
         }
       }
     }
   }
   if (!lists) return;
   __syncthreads();
+  // Determinism for ANY sampling map.  A list of up to LP entries is complete in shared memory: sorted by (p, tap) below,
+  // its first L entries go to the slots and the rest, in order, to one contiguous group of the overflow list.  For a list
+  // longer than LP, WHICH entries won a slot depends on the order of the atomics: one warp rebuilds it in (p, tap) order
+  // by scanning the taps of every output pixel (rare: LP is 12-15 at 38x63).  The fix-up kernel adds a group's entries
+  // in that order from one thread per channel.
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int q = warp; q < P.HWk; q += kBwdListThreads / 32) {
+      const int total = cnt[q];
+      if (total <= P.LP) continue;
+      const unsigned n_over = (unsigned)(total - P.L);
+      unsigned start = 0u;
+      if (lane == 0) {
+        start = atomicAdd(P.ovf_count, n_over);
+        const unsigned g = atomicAdd(P.ovf_count + 1, 1u);
+        if (g < P.ovf_gcap) P.ovf_groups[g] = make_uint4((unsigned)n, (unsigned)q, start, n_over);
+      }
+      start = __shfl_sync(0xffffffffu, start, 0);
+      int pos = 0;
+      for (int p0 = 0; p0 < P.HW; p0 += 32) {
+        const int p = p0 + lane;
+        bool hit[4] = {false, false, false, false};
+        float hw[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p < P.HW) {
+          const BwdTaps t = bwd_taps(P, n, p);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            hit[k] = t.ok[k] && t.w[k] != 0.0f && t.q[k] == q;
+            hw[k] = t.w[k];
+          }
+        }
+        const int nh = (int)hit[0] + (int)hit[1] + (int)hit[2] + (int)hit[3];
+        int incl = nh;                                   // inclusive prefix over the lanes = over p
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int j = pos + incl - nh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!hit[k]) continue;
+          if (j < P.L) {
+            w_s[(size_t)j * P.HWk + q] = hw[k];
+            o_s[(size_t)j * P.HWk + q] = (unsigned short)(((unsigned)p << 2) | (unsigned)k);
+          } else {
+            const unsigned e = start + (unsigned)(j - P.L);
+            if (e < P.ovf_cap) P.ovf[e] = make_uint4((unsigned)n, (unsigned)q, (unsigned)p, __float_as_uint(hw[k]));
+          }
+          ++j;
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+  }
+  __syncthreads();
   for (int q = tid; q < P.HWk; q += kBwdListThreads) {
+    const int held = min(cnt[q], P.LP);                   // entries of this list in shared memory
     const int c = min(cnt[q], P.L);
-    // sort the column by (p, tap): MXNet's sequential loop adds in exactly this order
-    for (int i = 1; i < c; ++i) {
+    // sort the column by (p, tap): MXNet's sequential loop adds in exactly this order (rebuilt columns already are)
+    for (int i = 1; i < held && cnt[q] <= P.LP; ++i) {
       const unsigned short ko = o_s[(size_t)i * P.HWk + q];
       const float kw = w_s[(size_t)i * P.HWk + q];
       int j = i - 1;
@@ -186,6 +244,17 @@ __global__ void __launch_bounds__(kBwdListThreads) bwd_lists_kernel(const __grid
       o_s[(size_t)(j + 1) * P.HWk + q] = ko;
       w_s[(size_t)(j + 1) * P.HWk + q] = kw;
     }
+    if (cnt[q] > P.L && cnt[q] <= P.LP) {                // the tail of a complete list: one ordered overflow group
+      const unsigned n_over = (unsigned)(cnt[q] - P.L);
+      const unsigned start = atomicAdd(P.ovf_count, n_over);
+      const unsigned g = atomicAdd(P.ovf_count + 1, 1u);
+      if (g < P.ovf_gcap) P.ovf_groups[g] = make_uint4((unsigned)n, (unsigned)q, start, n_over);
+      for (int i = P.L; i < cnt[q]; ++i) {
+        const unsigned e = start + (unsigned)(i - P.L);
+        const unsigned key = o_s[(size_t)i * P.HWk + q];
+        if (e < P.ovf_cap) P.ovf[e] = make_uint4((unsigned)n, (unsigned)q, key >> 2, __float_as_uint(w_s[(size_t)i * P.HWk + q]));
+      }
+    }
     P.ell_cnt[(size_t)n * P.HWk + q] = (unsigned char)c;
     for (int s = 0; s < P.L; ++s) {   // unused slots: weight 0, offset 0 (never read: loops stop at the count)
       const bool used = s < c;
@@ -195,16 +264,24 @@ __global__ void __launch_bounds__(kBwdListThreads) bwd_lists_kernel(const __grid
   }
 }
 
-// list entries that did not fit the L slots: grad_data[n,c,q] += w * og[n,c,p] for every channel
+// list entries that did not fit the L slots: one thread per (input pixel group, channel) adds the group's entries in
+// their (p, tap) order and then adds the sum to grad_data[n,c,q] - the only thread that touches that element after the
+// gather kernel: deterministic
 __global__ void __launch_bounds__(256) bwd_overflow_kernel(const __grid_constant__ BwdParams P) {
-  const unsigned cnt = min(*P.ovf_count, P.ovf_cap);
-  const long long total = (long long)cnt * P.C;
+  const unsigned groups = min(P.ovf_count[1], P.ovf_gcap);
+  const long long total = (long long)groups * P.C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned e = (unsigned)(i % cnt);
-    const int c = (int)(i / cnt);
-    const uint4 v = P.ovf[e];
-    const size_t fc = (size_t)v.x * P.C + c;
-    atomicAdd(P.gdata + fc * P.HWk + v.y, __uint_as_float(v.w) * __ldg(P.og + fc * P.HW + v.z));
+    const unsigned g = (unsigned)(i % groups);
+    const int c = (int)(i / groups);
+    const uint4 gr = P.ovf_groups[g];
+    const size_t fc = (size_t)gr.x * P.C + c;
+    const unsigned end = min(gr.z + gr.w, P.ovf_cap);
+    float acc = 0.f;
+    for (unsigned e = gr.z; e < end; ++e) {
+      const uint4 v = P.ovf[e];
+      acc = fmaf(__uint_as_float(v.w), __ldg(P.og + fc * P.HW + v.z), acc);
+    }
+    P.gdata[fc * P.HWk + gr.y] += acc;
   }
 }
 
@@ -540,7 +617,7 @@ constexpr int kBwdRegSlots = 6;   // list entries per input pixel kept in regist
 
 size_t bwd_workspace_bytes(int N, int HWk, int HW) {
   return r16((size_t)N * 4) + 16 + r16((size_t)N * HW * 16) + r16((size_t)N * kBwdMaxL * HWk * 2) +
-         r16((size_t)N * kBwdMaxL * HWk * 4) + r16((size_t)N * HWk) + (size_t)N * HW * 4 * 16;
+         r16((size_t)N * kBwdMaxL * HWk * 4) + r16((size_t)N * HWk) + (size_t)N * HW * 4 * 16 + (size_t)N * HWk * 16;
 }
 
 static bool plan_bwd_gather(BwdParams& P, size_t* smem_main, size_t* smem_lists, int* ppt_out) {
@@ -639,6 +716,17 @@ cudaError_t launch_sampler_backward(const float* data, const float* coords, int 
     ws += r16((size_t)P.N * P.HWk);
     P.ovf = reinterpret_cast<uint4*>(ws);
     P.ovf_cap = (unsigned)((size_t)P.N * P.HW * 4);
+    ws += (size_t)P.N * P.HW * 4 * 16;
+    P.ovf_groups = reinterpret_cast<uint4*>(ws);
+    P.ovf_gcap = (unsigned)((size_t)P.N * P.HWk);
+    {   // pre-pass slots: as many as fit the shared memory (complete lists need no rescan), at least L
+      const size_t cnt_bytes = (size_t)((P.HWk + 3) / 4 * 4) * 4;
+      long long lp = ((long long)227 * 1024 - (long long)cnt_bytes - 16) / ((long long)P.HWk * 6);
+      if (lp > 16) lp = 16;
+      if (lp < P.L) lp = P.L;
+      P.LP = (int)lp;
+      smem_lists = cnt_bytes + r16((size_t)P.LP * P.HWk * 6);
+    }
     e = cudaMemsetAsync(workspace, 0, r16((size_t)P.N * 4) + 16, st);   // claim counters + overflow count
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(bwd_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lists);

@@ -962,6 +962,31 @@ def test_gather_backward_overflowing_lists(ops, cuda):
     assert_close_f32(host(gg), want_g, scale=np.abs(want_g).max(), what="grad_grid")
 
 
+def test_gather_backward_is_deterministic_when_lists_overflow(ops, cuda):
+    """Lists longer than their slots are rebuilt in (p, tap) order by the pre-pass and their tail is added by one thread
+    per channel in that order: bit-identical from run to run for ANY sampling map - every pixel sampling one spot (a list
+    of H*W entries), integer flows (3x3 neighbourhoods with weights of 1e-6..1e-13), and +-6-cell random motion."""
+    rng = np.random.default_rng(61)
+    N, C, H, W = 3, 8, 38, 63
+    data = rng.standard_normal((N, C, H, W), dtype=np.float32)
+    og = rng.standard_normal((N, C, H, W), dtype=np.float32)
+    grid = np.zeros((N, 2, H, W), np.float32)
+    grid[0, 0], grid[0, 1] = 0.013, -0.2                                   # one spot
+    grid[1] = rng.uniform(-0.3, 0.3, size=(2, H, W)).astype(np.float32)    # everything lands in a third of the plane
+    grid[2] = rng.uniform(-1.1, 1.1, size=(2, H, W)).astype(np.float32)
+    runs = [ops.BilinearSampler_backward(dev(data, cuda), dev(grid, cuda), dev(og, cuda), kernel="gather") for _ in range(3)]
+    for gd, gg in runs[1:]:
+        assert np.array_equal(host(gd).view(np.uint32), host(runs[0][0]).view(np.uint32)), "grad_data differs between runs"
+    want_d, _ = O.bilinear_sampler_backward(data, grid, og)
+    assert np.abs(host(runs[0][0]) - want_d).max() <= 2e-5 * np.abs(want_d).max()
+    flow = np.round(rng.uniform(-6, 6, size=(N, 2, H, W))).astype(np.float32)   # integer flows
+    a = [ops.warp_backward(dev(data, cuda), dev(flow, cuda), dev(og, cuda), kernel="gather")[0] for _ in range(3)]
+    assert np.array_equal(host(a[0]).view(np.uint32), host(a[1]).view(np.uint32))
+    assert np.array_equal(host(a[0]).view(np.uint32), host(a[2]).view(np.uint32))
+    want_k, _ = O.warp_backward(data, flow, og)
+    assert_close_f32(host(a[0]), want_k, scale=np.abs(want_k).max(), what="integer flows, gather vs oracle")
+
+
 def test_warp_backward_and_grid_generator_backward(ops, cuda):
     d = make_case(21, 3, 8, 38, 63, max_px=96)
     rng = np.random.default_rng(22)

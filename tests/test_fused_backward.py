@@ -95,8 +95,10 @@ def test_gpu_backward_matches_oracle(cuda, shape, variant):
     for nme in want:
         # sums of C (logits, res) or N*H*W (rnet) products: the absolute part scales with the sum's own magnitude
         _close(got[nme].cpu().numpy(), want[nme], "%s grad_%s" % (variant, nme), rtol=2e-5, atol_frac=2e-5)
-        if nme != "flow":   # d/d(flow): per-CTA partial sums over channels are combined atomically (sampler_backward.cu);
-            # everything else, d/d(key) with overflowing gather lists included, is summed in a fixed order
+        if nme not in ("key", "flow"):   # those two come from the a7/a8 backward: d/d(flow) combines per-CTA partial sums
+            # atomically, and d/d(key) is summed in a fixed order only where the gather kernel serves the shape (planes
+            # whose slices are 16-byte addressable; tests/test_gpu_parity.py checks its determinism) - the scatter
+            # fallback of the other shapes adds atomically
             assert torch.equal(got[nme], again[nme]), "grad_%s is not deterministic" % nme
 
 

@@ -20,6 +20,8 @@
 namespace lsfa {
 
 cudaError_t launch_agg_records(const AggParams& P, uint4* rec, cudaStream_t st);   // aggregate_nchw.cu
+bool plan_tma_kernel(AggParams& P, size_t* smem_out);
+cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t st);
 
 constexpr int kTailThreads = 128;   // pixels per block
 constexpr int kTailCH = 32;         // channels per block
@@ -54,54 +56,76 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
   const int kn = key_slot(P, n);
   float T1 = 0.f, T2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
   const int c_begin = chunk * kTailCH, c_end = min(P.C, c_begin + kTailCH);
-  for (int c = c_begin; c < c_end; ++c) {
-    const size_t e = ((size_t)n * P.C + c) * P.HW + p;
-    const float g = active ? __ldg(Q.og + e) : 0.f;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // this thread's share of the rnet parameter gradients
-    if (active) {
-      if (byp) {          // ChooseFeat kept conv_feat: the whole gradient goes to cur
-        if (Q.gcur) put(Q.gcur + e, g, Q.add_cur);
-        if (Q.gw) Q.gw[e] = 0.f;
-        if (Q.gscale) put(Q.gscale + e, 0.f, Q.add_scale);
-      } else {
-        const unsigned char* plane = reinterpret_cast<const unsigned char*>(static_cast<const float*>(P.key) + ((size_t)kn * P.C + c) * P.HWk);
-        const float v00 = __ldg(reinterpret_cast<const float*>(plane + (o_top & 0xffffu)));
-        const float v01 = __ldg(reinterpret_cast<const float*>(plane + (o_top >> 16)));
-        const float v10 = __ldg(reinterpret_cast<const float*>(plane + (o_bot & 0xffffu)));
-        const float v11 = __ldg(reinterpret_cast<const float*>(plane + (o_bot >> 16)));
-        float vf = w00 * v00;                               // = ww * warp (the forward's folded chain)
-        vf = fmaf(w01, v01, vf);
-        vf = fmaf(w10, v10, vf);
-        vf = fmaf(w11, v11, vf);
-        const float sc = has_scale ? __ldg(static_cast<const float*>(P.scale) + e) : 1.0f;
-        float src0f = vf * sc;
-        const float wg = ww * g;
-        if (has_res) {
-          const float rw0 = __ldg(P.rnet_w + (size_t)c * 3), rw1 = __ldg(P.rnet_w + (size_t)c * 3 + 1), rw2 = __ldg(P.rnet_w + (size_t)c * 3 + 2);
-          src0f = fmaf(ww, rnet_term(rw0, rw1, rw2, __ldg(P.rnet_b + c), r0, r1, r2), src0f);
-          gr0 = fmaf(wg, rw0, gr0);
-          gr1 = fmaf(wg, rw1, gr1);
-          gr2 = fmaf(wg, rw2, gr2);
-          a0 = wg * r0; a1 = wg * r1; a2 = wg * r2; a3 = wg;
-        }
-        if (Q.gscale) put(Q.gscale + e, g * vf, Q.add_scale);
-        if (Q.gw) Q.gw[e] = wg * sc;
-        if (Q.gcur) put(Q.gcur + e, wc * g, Q.add_cur);
-        T1 = fmaf(g, src0f, T1);
-        if (Q.partT && has_cur) T2 = fmaf(g, __ldg(static_cast<const float*>(P.cur) + e), T2);
-      }
-    }
-    if (Q.partRnet) {    // block-wide sums of a0..a3 for this channel: warp shuffles, then one slot per warp
+  // four channels per step: all streaming loads of the step are issued before its stores (the outputs may alias the
+  // ww*warp buffer, so the compiler will not hoist them itself): 16 independent loads in flight per thread
+  constexpr int U = 4;
+  for (int c0 = c_begin; c0 < c_end; c0 += U) {
+    float gv[U], vv[U], sv[U], cv[U];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u;
+      const bool ok = active && c < c_end;
+      const size_t e = ((size_t)n * P.C + min(c, P.C - 1)) * P.HW + (active ? p : 0);
+      gv[u] = ok ? __ldg(Q.og + e) : 0.f;
+      vv[u] = (ok && !byp && Q.vf != nullptr) ? Q.vf[e] : 0.f;
+      sv[u] = (ok && !byp && has_scale) ? __ldg(static_cast<const float*>(P.scale) + e) : 1.0f;
+      cv[u] = (ok && !byp && Q.partT && has_cur) ? __ldg(static_cast<const float*>(P.cur) + e) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u;
+      if (c >= c_end) break;                                 // uniform
+      const size_t e = ((size_t)n * P.C + c) * P.HW + p;
+      const float g = gv[u];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // this thread's share of the rnet parameter gradients
+      if (active) {
+        if (byp) {          // ChooseFeat kept conv_feat: the whole gradient goes to cur
+          if (Q.gcur) put(Q.gcur + e, g, Q.add_cur);
+          if (Q.gw) Q.gw[e] = 0.f;
+          if (Q.gscale) put(Q.gscale + e, 0.f, Q.add_scale);
+        } else {
+          float vf = vv[u];                                   // = ww * warp (the forward's folded chain), from the all-TMA pass
+          if (Q.vf == nullptr) {                              // shapes that pass does not serve: gather here
+            const unsigned char* plane = reinterpret_cast<const unsigned char*>(static_cast<const float*>(P.key) + ((size_t)kn * P.C + c) * P.HWk);
+            const float v00 = __ldg(reinterpret_cast<const float*>(plane + (o_top & 0xffffu)));
+            const float v01 = __ldg(reinterpret_cast<const float*>(plane + (o_top >> 16)));
+            const float v10 = __ldg(reinterpret_cast<const float*>(plane + (o_bot & 0xffffu)));
+            const float v11 = __ldg(reinterpret_cast<const float*>(plane + (o_bot >> 16)));
+            vf = w00 * v00;
+            vf = fmaf(w01, v01, vf);
+            vf = fmaf(w10, v10, vf);
+            vf = fmaf(w11, v11, vf);
+          }
+          const float sc = sv[u];
+          float src0f = vf * sc;
+          const float wg = ww * g;
+          if (has_res) {
+            const float rw0 = __ldg(P.rnet_w + (size_t)c * 3), rw1 = __ldg(P.rnet_w + (size_t)c * 3 + 1), rw2 = __ldg(P.rnet_w + (size_t)c * 3 + 2);
+            src0f = fmaf(ww, rnet_term(rw0, rw1, rw2, __ldg(P.rnet_b + c), r0, r1, r2), src0f);
+            gr0 = fmaf(wg, rw0, gr0);
+            gr1 = fmaf(wg, rw1, gr1);
+            gr2 = fmaf(wg, rw2, gr2);
+            a0 = wg * r0; a1 = wg * r1; a2 = wg * r2; a3 = wg;
+          }
+          if (Q.gscale) put(Q.gscale + e, g * vf, Q.add_scale);
+          if (Q.gw) Q.gw[e] = wg * sc;
+          if (Q.gcur) put(Q.gcur + e, wc * g, Q.add_cur);
+          T1 = fmaf(g, src0f, T1);
+          if (Q.partT && has_cur) T2 = fmaf(g, cv[u], T2);
+        }
       }
-      if (lane == 0) {
-        red[0][warp][c - c_begin] = a0; red[1][warp][c - c_begin] = a1;
-        red[2][warp][c - c_begin] = a2; red[3][warp][c - c_begin] = a3;
+      if (Q.partRnet) {    // block-wide sums of a0..a3 for this channel: warp shuffles, then one slot per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+          a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+        }
+        if (lane == 0) {
+          red[0][warp][c - c_begin] = a0; red[1][warp][c - c_begin] = a1;
+          red[2][warp][c - c_begin] = a2; red[3][warp][c - c_begin] = a3;
+        }
       }
     }
   }
@@ -173,7 +197,9 @@ size_t tail_backward_workspace_bytes(int N, int C, int HW, bool want_gw, bool wa
   const size_t chunks = (size_t)(C + kTailCH - 1) / kTailCH, tiles = (size_t)(HW + kTailThreads - 1) / kTailThreads;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   size_t b = up((size_t)N * HW * 32);                                   // records
-  if (want_gw) b += up((size_t)N * C * HW * 4);
+  b += up((size_t)N * C * HW * 4);                                      // ww * warp of the forward pass, then d/d(warp) in place
+  b += up((size_t)N * 16 * 4 + 64);                                     // work-claim counters of that pass
+  (void)want_gw;
   if (want_logits) b += up(chunks * N * 2 * HW * 4);
   if (want_res) b += up(chunks * N * 3 * HW * 4) + up((size_t)N * tiles * C * 16);
   return b;
@@ -190,7 +216,11 @@ cudaError_t launch_tail_backward(AggParams P, const TailBwdRequest& R, void* wor
   Q.gscale = R.grad_scale; Q.add_scale = R.add_scale;
   Q.gcur = R.grad_cur; Q.add_cur = R.add_cur;
   Q.tiles = (int)tiles;
-  if (R.want_gw) { Q.gw = reinterpret_cast<float*>(ws); ws += up((size_t)P.N * P.C * P.HW * 4); }
+  float* vfbuf = reinterpret_cast<float*>(ws);
+  ws += up((size_t)P.N * P.C * P.HW * 4);
+  unsigned* sched = reinterpret_cast<unsigned*>(ws);
+  ws += up((size_t)P.N * 16 * 4 + 64);
+  if (R.want_gw) Q.gw = vfbuf;
   if (R.grad_logits) { Q.partT = reinterpret_cast<float*>(ws); ws += up(chunks * P.N * 2 * P.HW * 4); }
   if (R.grad_res || R.grad_rnet_w) {
     Q.partRes = reinterpret_cast<float*>(ws); ws += up(chunks * P.N * 3 * P.HW * 4);
@@ -199,9 +229,26 @@ cudaError_t launch_tail_backward(AggParams P, const TailBwdRequest& R, void* wor
   // the forward's sampling records (index math of a3-a8 + blend weights), once per output pixel
   P.records = nullptr; P.rowrange = nullptr; P.sched = nullptr;
   P.parts = 1; P.part_pix = P.HW;
+  // ww * warp by a warp-only pass of the all-TMA forward kernel over the SAME (folded) records, written where d/d(warp)
+  // will go: the tail kernel is then a pure streaming kernel (its own gather from global memory was 4 scattered loads per
+  // element: 1.7 ms per 64 frames; 0.24 ms + a streaming pass this way).  Shapes that kernel does not serve gather here.
+  AggParams F = P;
+  F.scale = nullptr; F.cur = nullptr; F.res = nullptr; F.rnet_w = nullptr; F.rnet_b = nullptr;
+  // F.bypass stays: bypass frames have no records (the pre-pass skips them) and the tail ignores their ww * warp
+  F.mode = LSFA_W_NONE; F.req_add = 0; F.out = vfbuf; F.logits = nullptr; F.emb_warp = nullptr; F.emb_cur = nullptr;
+  size_t fsmem = 0;
+  const bool staged = plan_tma_kernel(F, &fsmem) && F.parts == 1;
+  P.canon = staged ? 1 : 0;
   cudaError_t e = launch_agg_records(P, rec, st);
   if (e != cudaSuccess) return e;
   P.records = rec;
+  if (staged) {
+    F.records = rec;
+    F.records_ready = 1;
+    F.sched = sched;
+    if ((e = launch_agg_nchw_tma(F, fsmem, st)) != cudaSuccess) return e;
+    Q.vf = vfbuf;
+  }
   Q.P = P;
   dim3 grid((unsigned)tiles, (unsigned)chunks, (unsigned)P.N);
   agg_tail_backward_kernel<<<grid, kTailThreads, 0, st>>>(Q);

@@ -7,6 +7,8 @@ namespace lsfa {
 struct TailBwdParams {
   AggParams P;            // the forward's parameters, records filled in
   const float* og;        // d/d(out)
+  const float* vf;        // ww * warp of every element from a warp-only pass of the all-TMA forward kernel (may alias gw:
+                          // an element is read before it is overwritten by the same thread), or NULL = gather here
   float* gw;              // d/d(warped feature) = ww * g * scale, or NULL
   float* gscale;          // d/d(scale_map) or NULL
   float* gcur;            // d/d(cur) or NULL

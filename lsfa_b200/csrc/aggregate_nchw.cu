@@ -330,11 +330,12 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
   if (grid > P.items) grid = P.items;
   // planes cut into pixel parts: each part loads only the key rows its taps read (found by the pre-pass);
   // needs whole rows / planes to stay 16-byte addressable
-  const bool trim = P.sched && P.records && P.parts > 1 && (P.HWk % 4) == 0 && knob("LSFA_NO_ROW_TRIM") == nullptr;
+  const bool trim = P.sched && P.records && !P.records_ready && P.parts > 1 && (P.HWk % 4) == 0 && knob("LSFA_NO_ROW_TRIM") == nullptr;
   P.rowrange = trim ? P.sched + (size_t)P.N * P.parts : nullptr;
   // small batches (the reference's batch-1 operating mode, BASELINE configs[0]): ONE cooperative launch - the kernel's own
   // consumers build the records before a grid-wide barrier; static work split, whole key planes: no pre-pass, no memset
-  P.coop = (P.records != nullptr && (long long)P.N * P.parts <= kCoopMaxVirtualFrames && knob("LSFA_TMA_NO_COOP") == nullptr) ? 1 : 0;
+  P.coop = (P.records != nullptr && !P.records_ready && (long long)P.N * P.parts <= kCoopMaxVirtualFrames &&
+            knob("LSFA_TMA_NO_COOP") == nullptr) ? 1 : 0;
   if (P.coop) {
     P.sched = nullptr;
     P.rowrange = nullptr;
@@ -344,7 +345,7 @@ cudaError_t launch_agg_nchw_tma(const AggParams& Pin, size_t smem, cudaStream_t 
     cudaError_t e = cudaMemsetAsync(P.sched, 0, (size_t)P.N * P.parts * sizeof(unsigned) * (trim ? 3 : 1), st);
     if (e != cudaSuccess) return e;
   }
-  if (P.records && !P.coop) {  // pre-pass writes the records, the streaming kernel follows in stream order
+  if (P.records && !P.coop && !P.records_ready) {  // pre-pass writes the records, the streaming kernel follows in stream order
     AggParams R = P;
     R.records = nullptr;
     cudaError_t e = launch_agg_records(R, const_cast<uint4*>(P.records), st);

@@ -796,7 +796,18 @@ static const char* make_maps(const void* x, const void* w, const ConvParams& P, 
 // 2-CTA form: grid = 2 x (clusters that can be co-resident), cluster dims are a compile-time attribute of the kernel
 template <int EPI>
 static const char* launch_epi2(const CUtensorMap& tmA, const CUtensorMap& tmB2, const ConvParams& P, cudaStream_t stream, bool* launched) {
-  static int max_clusters = -1;    // benign race: idempotent
+  // per device: the shared-memory opt-in is a per-device attribute and the cluster occupancy a per-device fact
+  // (benign race between host threads: both compute the same values)
+  static int max_clusters_dev[64];
+  static bool known[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int& max_clusters = max_clusters_dev[dev];
+  if (!known[dev]) {
+    max_clusters = -1;
+    known[dev] = true;
+  }
   auto kfn = conv_gemm_tc2_kernel<EPI>;
   if (max_clusters < 0) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES) != cudaSuccess) {
@@ -830,11 +841,14 @@ static const char* launch_epi2(const CUtensorMap& tmA, const CUtensorMap& tmB2, 
 
 template <int EPI>
 static const char* launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& P, int sms, cudaStream_t stream) {
-  static bool attr_set = false;    // benign race: the attribute is idempotent
-  if (!attr_set) {
+  static bool attr_set[64];        // per device; benign race: the attribute is idempotent
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     if (cudaFuncSetAttribute(conv_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
       return "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int grid = P.num_items < sms ? P.num_items : sms;
   conv_gemm_tc_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, P);

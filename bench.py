@@ -524,7 +524,7 @@ def run_extras(dev, d, args):
     except Exception as e:
         out["fused_bf16_nhwc"] = {"error": repr(e)}
     for name, fn in (("cfg1_single_frame", extra_cfg1), ("cfg4_hires_68x120", extra_cfg4), ("cfg5_multi_stream", extra_cfg5),
-                     ("keyframe_networks_tcgen05", extra_keyframe)):
+                     ("keyframe_networks_tcgen05", extra_keyframe), ("backward_training_path", extra_backward)):
         torch.cuda.empty_cache()
         try:
             out[name] = fn(dev, d, peak, steps)
@@ -653,6 +653,30 @@ def extra_cfg5(dev, d, peak, steps):
     return {"streams": S, "frames_per_step": frames, "launches_per_step": len(slots), "ms_per_step": ms, "frames_per_s": fps,
             "alg_bytes_per_frame": alg, "achieved_gbs": fps * alg / 1e9, "frac_of_measured_peak": fps * alg / 1e9 / peak,
             "key_table_gb": sch.key_table.numel() * 4 / 1e9}
+
+
+def extra_backward(dev, d, peak, steps):
+    """SURVEY 8f rank 4 (get_train_symbol SYM:306-338): backward of GridGenerator(warp)+BilinearSampler as a gather
+    (deterministic d/d(key)), and of the fused operator with its tails, 64 frames of 1024x38x63 fp32; algorithmic bytes =
+    every stream once (3F / 2F for the sampler, 10F for the fused V2 backward incl. its d/d(warp) intermediate)."""
+    import torch
+
+    from lsfa_b200 import ops
+    F4, HW = C * H * W * 4, H * W
+    n = d["key"].shape[0]
+    flow = ops.mv_pool(d["mv"])
+    og = torch.randn_like(d["key"])
+    gk, gf = torch.empty_like(d["key"]), torch.empty_like(flow)
+    ws = torch.empty(ops.A.load().lsfa_bilinear_sampler_backward_workspace_bytes(n, C, H, W, H, W), dtype=torch.uint8, device=dev)
+    r = {"frames": n}
+    for tag, fn, alg in (
+            ("warp_backward_key_and_flow", lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, grad_flow=gf, workspace=ws, kernel="gather"), 3 * F4 + 16 * HW),
+            ("warp_backward_key_only", lambda: ops.warp_backward(d["key"], flow, og, grad_key=gk, req_flow="null", workspace=ws, kernel="gather"), 2 * F4 + 8 * HW),
+            ("fused_v2_backward_all_gradients", lambda: ops.warp_scale_aggregate_backward(og, d["key"], flow, flow_kind="flow", cur=d["cur"], scale_map=d["scale_map"], weight_mode="logits", logits=d["logits"]), 10 * F4)):
+        ms = time_launches(fn, 2, 10)
+        gb = n * alg / (ms / 1e3) / 1e9
+        r[tag] = {"ms_per_step": ms, "frames_per_s": n / (ms / 1e3), "achieved_gbs": gb, "frac_of_measured_peak": gb / peak}
+    return r
 
 
 def extra_keyframe(dev, d, peak, steps):

@@ -1,10 +1,13 @@
 // agg_nhwc_win_kernel - channels-last, window-resident form of the fused operator (tensor-map TMA).
 //
 // Why a third channels-last kernel.  The gather-by-bulk-copy kernel (aggregate_nhwc_tma.cuh) fetches the four taps of
-// every output pixel from L2: 4 x the key bytes per frame.  ncu (profiles/r2_ncu_nhwc_variants_l2.txt): every channels-last
-// variant then sits at 10.7-11.6 TB/s of L2 traffic whatever its DRAM traffic - the L2 slices' throughput cap, not HBM -
-// which is 0.72 (warp only, bf16) / 0.75 (shipped non-key path, bf16) of the copy peak.  Neighbouring output pixels sample
-// neighbouring key pixels, so this kernel loads ONE window of key pixels per 8x8 output tile and gathers from shared memory:
+// every output pixel from L2: 4 x the key bytes per frame, 10.7-11.6 TB/s of L2 -> SM traffic for every channels-last
+// variant (profiles/r2_ncu_nhwc_variants_l2.txt), close to what the L2 slices deliver.  This kernel was built to test
+// whether that is what holds the bf16 warp-only / shipped-path variants at 0.73 / 0.76 of the copy peak: neighbouring
+// output pixels sample neighbouring key pixels, so it loads ONE window of key pixels per 8x8 output tile and gathers
+// from shared memory.  Outcome: L2 -> SM traffic 1.27 -> 0.81 GB per 64 frames, bit-identical results,
+// the SAME time - L2 was not the limiter (the consumers' instruction stream is) - so the launcher never picks this
+// kernel by itself; it is reachable with force_generic = 5 and kept as the lower-traffic form.
 //
 //   work item  = (frame, 8x8 output tile), channel chunks of 256 bytes per pixel streamed through a stage ring
 //   window     = 12 x 12 key pixels x 256 B, ONE cp.async.bulk.tensor.4d per stage from a (C, Wk, Hk, keys) tensor map:

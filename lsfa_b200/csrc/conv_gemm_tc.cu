@@ -17,14 +17,17 @@
 //     columns fill the SM's 512 tensor-memory columns; per 64-deep k-step the CTA loads 2 x 16 KB of
 //     activations + 32 KB of weights for 2 x 128 x 256 x 64 MACs (128 flop per byte of L2 traffic).
 //   * warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane), warp 2 = tensor-memory
-//     allocator, warps 4-7 = epilogue: thread r owns accumulator row r (tcgen05.ld 32x32b), so every per-pixel
-//     reduction over channels is a private register sum - no shuffles, no shared memory.
+//     allocator, warps 4-11 = epilogue (two per tensor-memory lane quarter): thread r owns accumulator row r
+//     (tcgen05.ld 32x32b), so every per-pixel reduction over channels is a private register sum - no shuffles.
+//   * conv_gemm_tc2_kernel (further down) is the CTA-pair form of the same work item for the STORE / NQ epilogues:
+//     tcgen05.mma.cta_group::2, half of the weight tile per CTA, double-buffered accumulators.
 //   * epilogues: bias(+ReLU) -> bf16 store (em_conv1/2);  COSINE (em_conv3): sum e_cur^2, sum e_warp^2,
 //     sum e_warp*e_cur over this CTA's 256 output channels -> 3 floats per pixel; the 2048-channel embeddings
 //     never leave the SM (the reference round-trips 2 x 19.6 MB per frame through HBM for them);
 //     NQ (Nq_conv1): bias+ReLU, then the 256->16 (+ReLU) ->1 tail per pixel in registers -> the logit itself.
 //
-// SASS of this file shows UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (cp.async.bulk.tensor), SYNCS (mbarrier).
+// SASS of this file shows UTCHMMA / UTCHMMA.2CTA (tcgen05.mma), UTCBAR.2CTA.MULTICAST (tcgen05.commit), LDTM (tcgen05.ld),
+// UTMALDG / UTMALDG.2CTA (cp.async.bulk.tensor), SYNCS (mbarrier).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>

@@ -36,7 +36,14 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
   const bool active = p < P.HW;
   const bool byp = P.bypass != nullptr && __ldg(P.bypass + n) != 0;
   const bool has_scale = P.scale != nullptr, has_res = P.res != nullptr, has_cur = P.mode != LSFA_W_NONE;
-  __shared__ float red[4][kTailThreads / 32][kTailCH];   // rnet: per-warp partial sums of 4 quantities per channel
+  // rnet parameter gradients: d/d(W)[c][j] = sum_p ww*g[p,c] * res[j][p], d/d(b)[c] = sum_p ww*g[p,c] - a (32 x 128) by
+  // (128 x 4) product per block.  ww*g goes to a padded shared tile and the block multiplies once at the end (a warp
+  // shuffle tree per channel and quantity was 20 SHFL + 20 FADD per channel and thread: half of this kernel's instructions)
+  // (dynamic shared memory, allocated only when these gradients are wanted: 18 KB per block would cost the other variants
+  // a fifth of their resident warps)
+  extern __shared__ float tail_smem[];
+  float (*wgT)[kTailThreads + 1] = reinterpret_cast<float (*)[kTailThreads + 1]>(tail_smem);
+  float (*rS)[kTailThreads] = reinterpret_cast<float (*)[kTailThreads]>(tail_smem + kTailCH * (kTailThreads + 1));
 
   float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f, wc = 0.f, ww = 0.f;
   unsigned o_top = 0u, o_bot = 0u;
@@ -54,6 +61,7 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
     r2 = __ldg(P.res + ((size_t)n * 3 + 2) * P.HW + p);
   }
   const int kn = key_slot(P, n);
+  if (Q.partRnet) { rS[0][tid] = r0; rS[1][tid] = r1; rS[2][tid] = r2; }
   float T1 = 0.f, T2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
   const int c_begin = chunk * kTailCH, c_end = min(P.C, c_begin + kTailCH);
   // four channels per step: all streaming loads of the step are issued before its stores (the outputs may alias the
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
       if (c >= c_end) break;                                 // uniform
       const size_t e = ((size_t)n * P.C + c) * P.HW + p;
       const float g = gv[u];
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // this thread's share of the rnet parameter gradients
+      float a3 = 0.f;                                      // ww * g: this thread's share of the rnet parameter gradients
       if (active) {
         if (byp) {          // ChooseFeat kept conv_feat: the whole gradient goes to cur
           if (Q.gcur) put(Q.gcur + e, g, Q.add_cur);
@@ -105,7 +113,7 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
             gr0 = fmaf(wg, rw0, gr0);
             gr1 = fmaf(wg, rw1, gr1);
             gr2 = fmaf(wg, rw2, gr2);
-            a0 = wg * r0; a1 = wg * r1; a2 = wg * r2; a3 = wg;
+            a3 = wg;
           }
           if (Q.gscale) put(Q.gscale + e, g * vf, Q.add_scale);
           if (Q.gw) Q.gw[e] = wg * sc;
@@ -114,19 +122,7 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
           if (Q.partT && has_cur) T2 = fmaf(g, cv[u], T2);
         }
       }
-      if (Q.partRnet) {    // block-wide sums of a0..a3 for this channel: warp shuffles, then one slot per warp
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-          a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-          a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-        }
-        if (lane == 0) {
-          red[0][warp][c - c_begin] = a0; red[1][warp][c - c_begin] = a1;
-          red[2][warp][c - c_begin] = a2; red[3][warp][c - c_begin] = a3;
-        }
-      }
+      if (Q.partRnet) wgT[c - c_begin][tid] = a3;          // ww * g of this pixel and channel (0 for bypass / inactive)
     }
   }
   if (active) {
@@ -143,10 +139,13 @@ __global__ void __launch_bounds__(kTailThreads) agg_tail_backward_kernel(const _
   if (Q.partRnet) {
     __syncthreads();
     for (int i = tid; i < 4 * (c_end - c_begin); i += kTailThreads) {
-      const int q = i / (c_end - c_begin), cc = i % (c_end - c_begin);
+      const int cc = i >> 2, q = i & 3;
       float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < kTailThreads / 32; ++w) s += red[q][w][cc];
+      if (q < 3) {
+        for (int pp = 0; pp < kTailThreads; ++pp) s = fmaf(wgT[cc][pp], rS[q][pp], s);
+      } else {
+        for (int pp = 0; pp < kTailThreads; ++pp) s += wgT[cc][pp];
+      }
       Q.partRnet[(((size_t)n * Q.tiles + tile) * P.C + (c_begin + cc)) * 4 + q] = s;
     }
   }
@@ -251,7 +250,8 @@ cudaError_t launch_tail_backward(AggParams P, const TailBwdRequest& R, void* wor
   }
   Q.P = P;
   dim3 grid((unsigned)tiles, (unsigned)chunks, (unsigned)P.N);
-  agg_tail_backward_kernel<<<grid, kTailThreads, 0, st>>>(Q);
+  const size_t tail_smem_bytes = Q.partRnet ? (size_t)(kTailCH * (kTailThreads + 1) + 3 * kTailThreads) * sizeof(float) : 0;
+  agg_tail_backward_kernel<<<grid, kTailThreads, tail_smem_bytes, st>>>(Q);
   if ((e = cudaPeekAtLastError()) != cudaSuccess) return e;
   const size_t NP = (size_t)P.N * P.HW;
   if (R.grad_logits)

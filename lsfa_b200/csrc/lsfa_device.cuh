@@ -76,6 +76,7 @@ struct AggParams {
   const uint4* records;        // per-pixel packed sampling records (N*HW x 32 B) from the pre-pass, or NULL
   int canon;                   // the record pre-pass writes canonical_taps() records (warp-only variant of the all-TMA kernel)
   int records_ready;           // `records` already hold this launch's records (tail backward: the forward's folded weights)
+  unsigned* zero_counter;      // record pre-pass: the streaming kernel's work-claim counter, zeroed here (saves a memset node)
   int coop;                    // all-TMA NCHW kernel launched cooperatively: its own consumers build the records, then a
                                // grid-wide barrier - the one-launch form for small batches (no pre-pass, no memset)
   int rnet_smem;               // channels-last tile kernel: rnet weights staged in dynamic shared memory

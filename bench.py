@@ -558,15 +558,18 @@ def extra_cfg1(dev, d, peak, steps):
     r["fused_v2_us"] = 1e3 * ms
     r["fused_v2_launches"] = p2.launches
     for tag, p in (("fused_warp_graph_us", p0), ("fused_v2_graph_us", p2)):
+        # recorded and replayed through the C ABI (lsfa_graph_begin / _end / _launch), not through torch
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for _ in range(3):
                 p.run(side.cuda_stream)
             side.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
+            g = ops.RecordedGraph(side.cuda_stream)
+            with g:
                 p.run(side.cuda_stream)
-        r[tag] = 1e3 * time_launches(g.replay, 10, 200)
+        r[tag] = 1e3 * time_launches(lambda: g.launch(s), 10, 200)
+        g.close()
+    r["graph_api"] = "lsfa_graph_begin / lsfa_graph_end / lsfa_graph_launch (C ABI)"
     r["bytes_v0"] = 2 * F4 + 32 * HW
     r["frac_of_measured_peak_fused_warp_graph"] = r["bytes_v0"] / (r["fused_warp_graph_us"] * 1e-6) / 1e9 / peak
     # CPU side by side: torch.grid_sample (align_corners=True, zeros) = a7+a8 on the host cores

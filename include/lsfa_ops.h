@@ -407,6 +407,22 @@ LSFA_API int lsfa_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H,
 LSFA_API int lsfa_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_layout,
                       void* stream);
 
+/* ---- record / replay (BASELINE configs[0]: the reference's batch-1 mode pays a launch per operator and frame) ----
+ * Every entry point above only enqueues on the caller's stream - no allocation, no synchronisation, no host read-back -
+ * so a sequence of calls can be captured into a CUDA graph and replayed with one launch.  These four wrap the CUDA
+ * calls for callers that do not link the runtime themselves (MXNet's Python side: core/tester.py:138-145 issues the
+ * operators of a frame one by one).  The captured calls' buffers (arguments, workspace) must stay alive and in place
+ * for the lifetime of the graph; their CONTENTS may change between replays (new frame, same shapes).
+ *   lsfa_graph_begin(stream)            cudaStreamBeginCapture (thread-local mode)
+ *   ... any lsfa_* calls on `stream` ...
+ *   lsfa_graph_end(stream, &g)          cudaStreamEndCapture + cudaGraphInstantiate -> opaque handle
+ *   lsfa_graph_launch(g, stream)        cudaGraphLaunch        lsfa_graph_destroy(g)
+ * An error between begin and end invalidates the capture: lsfa_graph_end then returns LSFA_E_CUDA and *graph = NULL. */
+LSFA_API int lsfa_graph_begin(void* stream);
+LSFA_API int lsfa_graph_end(void* stream, void** graph);
+LSFA_API int lsfa_graph_launch(void* graph, void* stream);
+LSFA_API int lsfa_graph_destroy(void* graph);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,10 @@ PROTOTYPES = {
     "lsfa_warp_scale_aggregate_backward_f32_nchw": (_I, [C.POINTER(LsfaAggArgs), C.POINTER(LsfaAggGrads), _P]),
     "lsfa_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "lsfa_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "lsfa_graph_begin": (_I, [_P]),
+    "lsfa_graph_end": (_I, [_P, C.POINTER(C.c_void_p)]),
+    "lsfa_graph_launch": (_I, [_P, _P]),
+    "lsfa_graph_destroy": (_I, [_P]),
 }
 
 _lib = None

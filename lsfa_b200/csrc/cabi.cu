@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <new>
+
 #include "lsfa_device.cuh"
 #include "conv_gemm_tc.h"
 #include "aggregate_backward.h"
@@ -634,6 +636,52 @@ int lsfa_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, i
   return cuda_result(lsfa::launch_nhwc_to_nchw(src, dst, N, C, H * W, src_layout == LSFA_LAYOUT_NHWC_BF16,
                                                as_stream(stream)),
                      "nhwc_to_nchw launch");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// record / replay: the entry points only enqueue, so a frame's sequence of calls is one CUDA graph
+// ---------------------------------------------------------------------------------------------------------
+struct LsfaGraph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+int lsfa_graph_begin(void* stream) {
+  if (!stream) return fail(LSFA_E_BADARG, "capture needs an explicit (non-NULL) stream");
+  return cuda_result(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+}
+int lsfa_graph_end(void* stream, void** graph) {
+  if (!graph) return fail(LSFA_E_BADARG, "graph out-pointer is NULL");
+  *graph = nullptr;
+  if (!stream) return fail(LSFA_E_BADARG, "capture needs an explicit (non-NULL) stream");
+  cudaGraph_t g = nullptr;
+  if (int r = cuda_result(cudaStreamEndCapture(as_stream(stream), &g), "cudaStreamEndCapture")) return r;
+  if (!g) return fail(LSFA_E_CUDA, "the capture was invalidated by an error between lsfa_graph_begin and lsfa_graph_end");
+  cudaGraphExec_t ex = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g);
+    return cuda_result(e, "cudaGraphInstantiate");
+  }
+  LsfaGraph* h = new (std::nothrow) LsfaGraph{g, ex};
+  if (!h) {
+    cudaGraphExecDestroy(ex);
+    cudaGraphDestroy(g);
+    return fail(LSFA_E_BADARG, "out of host memory");
+  }
+  *graph = h;
+  return LSFA_OK;
+}
+int lsfa_graph_launch(void* graph, void* stream) {
+  if (!graph) return fail(LSFA_E_BADARG, "graph is NULL");
+  return cuda_result(cudaGraphLaunch(static_cast<LsfaGraph*>(graph)->exec, as_stream(stream)), "cudaGraphLaunch");
+}
+int lsfa_graph_destroy(void* graph) {
+  if (!graph) return LSFA_OK;
+  LsfaGraph* h = static_cast<LsfaGraph*>(graph);
+  cudaGraphExecDestroy(h->exec);
+  cudaGraphDestroy(h->graph);
+  delete h;
+  return LSFA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

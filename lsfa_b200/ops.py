@@ -235,13 +235,21 @@ def mv_prepare(mv_coviar: torch.Tensor, im_scale: float = 1.0, negate: bool = Tr
     return out
 
 
-def mv_pool(mv: torch.Tensor, im_scale: float = 1.0, mode="centre2x2") -> torch.Tensor:
-    """image.py:207-215,220-228 for the MV: (N,h,w,2) int32|f32 -> flow (N,2,ceil(h/16),ceil(w/16))."""
+def mv_pool(mv: torch.Tensor, im_scale: float = 1.0, mode="centre2x2", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """image.py:207-215,220-228 for the MV: (N,h,w,2) int32|f32 -> flow (N,2,ceil(h/16),ceil(w/16)) (``out``: a
+    caller-owned destination, e.g. inside a recorded graph)."""
     _dev(mv, "mv")
     if mv.dim() != 4 or mv.shape[3] != 2:
         raise ValueError("mv must be (N,h,w,2), got %s" % (tuple(mv.shape),))
     N, h, w, _ = mv.shape
-    flow = torch.empty((N, 2, _ceil16(h), _ceil16(w)), dtype=torch.float32, device=mv.device)
+    shape = (N, 2, _ceil16(h), _ceil16(w))
+    if out is None:
+        flow = torch.empty(shape, dtype=torch.float32, device=mv.device)
+    else:
+        _dev(out, "out", torch.float32)
+        if tuple(out.shape) != shape or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s float32 tensor, got %s" % (shape, tuple(out.shape)))
+        flow = out
     lib = A.load()
     if mv.dtype == torch.int32:
         fn = lib.lsfa_mv_pool_i32
@@ -477,6 +485,55 @@ class PreparedAggregate:
     def run(self, stream: Optional[int] = None) -> torch.Tensor:
         A.check(self._lib.lsfa_warp_scale_aggregate(self.args, _stream() if stream is None else stream))
         return self.out
+
+
+class RecordedGraph:
+    """A sequence of this package's calls recorded into ONE CUDA graph through the C ABI (``lsfa_graph_begin`` /
+    ``lsfa_graph_end`` / ``lsfa_graph_launch``): the reference issues the operators of a frame one by one
+    (core/tester.py:138-145); replaying them costs one launch.
+
+        g = RecordedGraph(stream)
+        with g:                       # every ops.* / PreparedAggregate.run(stream) call on `stream` is recorded
+            p.run(stream)
+        g.launch()                    # same buffers, new contents
+
+    The recorded calls' tensors must stay alive and in place for the lifetime of the graph."""
+
+    def __init__(self, stream: int):
+        if not stream:
+            raise ValueError("recording needs an explicit, non-default stream handle")
+        self._lib = A.load()
+        self.stream = stream
+        self._h = None
+
+    def __enter__(self):
+        A.check(self._lib.lsfa_graph_begin(self.stream))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        import ctypes
+        h = ctypes.c_void_p()
+        rc = self._lib.lsfa_graph_end(self.stream, ctypes.byref(h))
+        if et is None:
+            A.check(rc)
+            self._h = h
+        return False
+
+    def launch(self, stream: Optional[int] = None):
+        if self._h is None:
+            raise RuntimeError("nothing recorded")
+        A.check(self._lib.lsfa_graph_launch(self._h, self.stream if stream is None else stream))
+
+    def close(self):
+        if self._h is not None:
+            self._lib.lsfa_graph_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def warp_scale_aggregate_backward(out_grad, key, flow, *, want=("key", "flow", "scale", "cur", "logits", "res", "rnet"), **kw):

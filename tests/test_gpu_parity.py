@@ -987,6 +987,42 @@ def test_gather_backward_is_deterministic_when_lists_overflow(ops, cuda):
     assert_close_f32(host(a[0]), want_k, scale=np.abs(want_k).max(), what="integer flows, gather vs oracle")
 
 
+def test_recorded_graph_through_the_c_abi_replays_a_frame(ops, cuda):
+    """lsfa_graph_begin / _end / _launch: the three drop-in operators and the fused op of ONE frame (BASELINE configs[0])
+    recorded on a side stream, replayed with new input contents in the same buffers; results = the eager calls, bit for bit.
+    The one-launch cooperative form of the fused kernel is part of the recording."""
+    d = make_case(31, 1, 64, 38, 63)
+    key, mv, cur, sm, lg = (dev(d[k], cuda) for k in ("key", "mv", "cur", "scale_map", "logits"))
+    side = torch.cuda.Stream()
+    st = side.cuda_stream
+    grid = torch.empty((1, 2, 38, 63), device=cuda)
+    flow = torch.empty((1, 2, 38, 63), device=cuda)
+    out_s = torch.empty_like(key)
+    with torch.cuda.stream(side):
+        p = ops.PreparedAggregate(key, mv, flow_kind="raw", cur=cur, scale_map=sm, weight_mode="logits", logits=lg)
+        for _ in range(2):                                  # warm-up outside the recording (attribute opt-ins happen once)
+            p.run(st)
+            ops.BilinearSampler(key, ops.GridGenerator(ops.mv_pool(mv, out=flow), out=grid), out=out_s)
+        side.synchronize()
+        g = ops.RecordedGraph(st)
+        with g:
+            p.run(st)
+            ops.BilinearSampler(key, ops.GridGenerator(ops.mv_pool(mv, out=flow), out=grid), out=out_s)
+        for rep in range(3):
+            d2 = make_case(40 + rep, 1, 64, 38, 63)
+            for t, k in ((key, "key"), (mv, "mv"), (cur, "cur"), (sm, "scale_map"), (lg, "logits")):
+                t.copy_(dev(d2[k], cuda))
+            g.launch()
+            side.synchronize()
+            got_f, got_s = p.out.clone(), out_s.clone()
+            want_f = ops.warp_scale_aggregate(key, mv, flow_kind="raw", cur=cur, scale_map=sm, weight_mode="logits", logits=lg)
+            want_s = ops.BilinearSampler(key, ops.GridGenerator(ops.mv_pool(mv)))
+            side.synchronize()
+            assert torch.equal(got_f, want_f) and torch.equal(got_s, want_s), rep
+            assert_close_f32(host(got_f), oracle_fused(d2, O.W_LOGITS), scale=max(np.abs(d2["key"]).max(), np.abs(d2["cur"]).max()), what="replay %d" % rep)
+        g.close()
+
+
 def test_warp_backward_and_grid_generator_backward(ops, cuda):
     d = make_case(21, 3, 8, 38, 63, max_px=96)
     rng = np.random.default_rng(22)
